@@ -64,8 +64,8 @@ def camera_plane(R, t):
 def undistort_point_spec(u, v, K, dist):
     """cv2.undistortPoints(P=None) restated: exactly 5 fixed-point iterations."""
     k1, k2, p1, p2, k3 = [float(x) for x in np.asarray(dist).ravel()[:5]]
-    x0 = (float(u) - K[0, 2]) / K[0, 0]
-    y0 = (float(v) - K[1, 2]) / K[1, 1]
+    x0 = (float(u) - K[0, 2]) * (1.0 / K[0, 0])          # OpenCV multiplies by ifx = 1./fx: bit-exact this way
+    y0 = (float(v) - K[1, 2]) * (1.0 / K[1, 1])
     x, y = x0, y0
     for _ in range(5):
         r2 = x * x + y * y

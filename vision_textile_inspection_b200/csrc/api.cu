@@ -1,0 +1,363 @@
+// C-ABI glue of libvti.so: host-side planning (letterbox geometry, cv2 resize taps, undistort map, nearest-resize
+// multiplicity tables), handle lifetime, stage entry points.  See include/vti.h for the contract.
+//
+// Planning mirrors oracle/cv_fixed.py (bit-exact vs OpenCV) and ultralytics LetterBox geometry;
+// tests/test_abi_cpu.py checks these host functions against the oracle without a GPU.
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include "vti_internal.h"
+
+size_t vti_k3_smem_bytes(int cap);
+int vti_k3_prepare(int cap);
+
+static thread_local std::string g_err;
+void vti_set_error(const std::string& s) { g_err = s; }
+
+extern "C" const char* vti_last_error(void) { return g_err.c_str(); }
+extern "C" int vti_abi_version(void) { return 1; }
+
+// Python round(): half to even on a double
+static inline int py_round(double x) { return (int)nearbyint(x); }
+
+extern "C" int vti_plan_geometry(int frame_h, int frame_w, int imgsz, int stride, int max_det, int max_candidates,
+                                 vti_geometry* g) {
+    if (!g || frame_h <= 0 || frame_w <= 0 || imgsz <= 0 || stride <= 0 || (stride % 32) != 0) {
+        vti_set_error("vti_plan_geometry: bad argument (stride must be a multiple of 32)");
+        return VTI_EINVAL;
+    }
+    const double r = std::fmin((double)imgsz / frame_h, (double)imgsz / frame_w);
+    g->new_w = py_round(frame_w * r);
+    g->new_h = py_round(frame_h * r);
+    double dw = (double)(((imgsz - g->new_w) % stride + stride) % stride) / 2.0;
+    double dh = (double)(((imgsz - g->new_h) % stride + stride) % stride) / 2.0;
+    g->top = py_round(dh - 0.1); g->bottom = py_round(dh + 0.1);
+    g->left = py_round(dw - 0.1); g->right = py_round(dw + 0.1);
+    g->LH = g->new_h + g->top + g->bottom;
+    g->LW = g->new_w + g->left + g->right;
+    if (g->LH % 32 || g->LW % 32) {
+        vti_set_error("vti_plan_geometry: letterboxed size is not a multiple of 32");
+        return VTI_EINVAL;
+    }
+    g->ph = g->LH / 4; g->pw = g->LW / 4;
+    g->A = 0;
+    for (int l = 0; l < 3; ++l) {
+        g->lvl_h[l] = g->LH / (8 << l);
+        g->lvl_w[l] = g->LW / (8 << l);
+        g->A += g->lvl_h[l] * g->lvl_w[l];
+    }
+    g->mask_words = g->LW / 32;
+    int cap = max_candidates > 0 ? max_candidates : VTI_CAND_CAP_MAX;
+    if (cap > g->A) cap = g->A;
+    if (cap > VTI_CAND_CAP_MAX) cap = VTI_CAND_CAP_MAX;
+    g->max_candidates = cap;
+    g->max_det = max_det;
+    return VTI_OK;
+}
+
+// cv2.resize INTER_LINEAR coefficient tables (oracle/cv_fixed.py linear_taps_x / linear_taps_y)
+static void taps_core(int sn, int dn, int d, int* s_out, float* f_out) {
+    const double scale = 1.0 / ((double)dn / (double)sn);
+    float f = (float)((d + 0.5) * scale - 0.5);
+    const int s = (int)std::floor(f);
+    f -= (float)s;
+    *s_out = s;
+    *f_out = f;
+}
+
+extern "C" int vti_plan_resize_taps_x(int sn, int dn, int32_t* idx, int16_t* a0, int16_t* a1) {
+    for (int d = 0; d < dn; ++d) {
+        int s; float f;
+        taps_core(sn, dn, d, &s, &f);
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+        idx[d] = s;
+        a0[d] = (int16_t)lrintf((1.f - f) * 2048.f);
+        a1[d] = (int16_t)lrintf(f * 2048.f);
+    }
+    return VTI_OK;
+}
+
+extern "C" int vti_plan_resize_taps_y(int sn, int dn, int32_t* i0, int32_t* i1, int16_t* b0, int16_t* b1) {
+    for (int d = 0; d < dn; ++d) {
+        int s; float f;
+        taps_core(sn, dn, d, &s, &f);
+        i0[d] = s < 0 ? 0 : (s > sn - 1 ? sn - 1 : s);
+        i1[d] = s + 1 < 0 ? 0 : (s + 1 > sn - 1 ? sn - 1 : s + 1);
+        b0[d] = (int16_t)lrintf((1.f - f) * 2048.f);
+        b1[d] = (int16_t)lrintf(f * 2048.f);
+    }
+    return VTI_OK;
+}
+
+extern "C" int vti_plan_undistort_map(const double K[9], const double dist[5], int h, int w, int32_t* ix, int32_t* iy) {
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double k1 = dist[0], k2 = dist[1], p1 = dist[2], p2 = dist[3], k3 = dist[4];
+    for (int v = 0; v < h; ++v) {
+        const double y = ((double)v - cy) / fy;
+        for (int u = 0; u < w; ++u) {
+            const double x = ((double)u - cx) / fx;
+            const double x2 = x * x, y2 = y * y;
+            const double r2 = x2 + y2;
+            const double _2xy = 2.0 * x * y;
+            const double kr = 1.0 + ((k3 * r2 + k2) * r2 + k1) * r2;
+            const double xd = x * kr + p1 * _2xy + p2 * (r2 + 2.0 * x2);
+            const double yd = y * kr + p1 * (r2 + 2.0 * y2) + p2 * _2xy;
+            const double mx = fx * xd + cx, my = fy * yd + cy;
+            ix[(size_t)v * w + u] = (int32_t)nearbyint(mx * 32.0);
+            iy[(size_t)v * w + u] = (int32_t)nearbyint(my * 32.0);
+        }
+    }
+    return VTI_OK;
+}
+
+extern "C" int vti_plan_nearest_map(int dst_n, int src_n, int32_t* map) {
+    const double ifx = 1.0 / ((double)dst_n / (double)src_n);
+    for (int d = 0; d < dst_n; ++d) {
+        int s = (int)std::floor(d * ifx);
+        map[d] = s < src_n - 1 ? s : src_n - 1;
+    }
+    return VTI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& v) {
+    VTI_CUDA(cudaMalloc((void**)dptr, sizeof(T) * (v.empty() ? 1 : v.size())));
+    if (!v.empty()) VTI_CUDA(cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return VTI_OK;
+}
+
+static int build_axis_lut(int frame_n, int lb_n, AxisLut* lut, int32_t** d_map) {
+    std::vector<int32_t> map(frame_n), cnt(lb_n, 0), sum(lb_n, 0), first(lb_n, INT_MAX), last(lb_n, -1);
+    vti_plan_nearest_map(frame_n, lb_n, map.data());
+    for (int d = 0; d < frame_n; ++d) {
+        const int s = map[d];
+        cnt[s]++;
+        sum[s] += d;
+        if (d < first[s]) first[s] = d;
+        if (d > last[s]) last[s] = d;
+    }
+    int rc;
+    if ((rc = upload(&lut->cnt, cnt))) return rc;
+    if ((rc = upload(&lut->sum, sum))) return rc;
+    if ((rc = upload(&lut->first, first))) return rc;
+    if ((rc = upload(&lut->last, last))) return rc;
+    if (d_map) return upload(d_map, map);
+    return VTI_OK;
+}
+
+extern "C" void vti_destroy(vti_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->d_tap_x_idx, h->d_tap_x_a, h->d_tap_y_i, h->d_tap_y_b, h->d_und_lut, h->lutY.cnt, h->lutY.sum,
+                    h->lutY.first, h->lutY.last, h->lutX.cnt, h->lutX.sum, h->lutX.first, h->lutX.last, h->d_xmap,
+                    h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
+                    h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
+                    h->d_counts, h->d_results};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int vti_create(const vti_params* p, vti_handle** out) {
+    if (!p || !out) { vti_set_error("vti_create: null argument"); return VTI_EINVAL; }
+    *out = nullptr;
+    if (p->struct_size != (int32_t)sizeof(vti_params)) {
+        vti_set_error("vti_create: vti_params.struct_size mismatch (ABI)");
+        return VTI_EINVAL;
+    }
+    if (p->nc < 1 || p->nc > 255 || p->max_det < 1 || p->max_det > 1024 || p->max_batch < 1 || p->neighborhood < 0 ||
+        p->neighborhood > 7 || (p->variant != 0 && p->variant != 1)) {
+        vti_set_error("vti_create: parameter out of range (nc 1..255, max_det 1..1024, neighborhood 0..7, variant 0/1)");
+        return VTI_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        vti_set_error("vti_create: no CUDA device -- this library has no CPU fallback");
+        return VTI_ENODEV;
+    }
+    vti_handle* h = new vti_handle();
+    std::memset((void*)h, 0, sizeof(*h));
+    h->p = *p;
+    int rc = vti_plan_geometry(p->frame_h, p->frame_w, p->imgsz, p->stride, p->max_det, p->max_candidates, &h->g);
+    if (rc) { delete h; return rc; }
+    VTI_CUDA(cudaGetDevice(&h->device));
+    VTI_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    const vti_geometry& g = h->g;
+    const int fh = p->frame_h, fw = p->frame_w;
+
+    // ---- K1 tables
+    std::vector<int32_t> xi(g.new_w), yi(2 * (size_t)g.new_h);
+    std::vector<int16_t> xa(2 * (size_t)g.new_w), yb(2 * (size_t)g.new_h);
+    if (fw == 2 * g.new_w && fh == 2 * g.new_h) {
+        h->resize_mode = 2;                                  // OpenCV's silent INTER_AREA switch
+        for (int d = 0; d < g.new_w; ++d) { xi[d] = 2 * d; xa[2 * d] = 1; xa[2 * d + 1] = 1; }
+        for (int d = 0; d < g.new_h; ++d) { yi[2 * d] = 2 * d; yi[2 * d + 1] = 2 * d + 1; yb[2 * d] = 1; yb[2 * d + 1] = 1; }
+    } else {
+        h->resize_mode = 1;
+        std::vector<int32_t> i0(g.new_h), i1(g.new_h);
+        std::vector<int16_t> a0(g.new_w), a1(g.new_w), b0(g.new_h), b1(g.new_h);
+        if (fw == g.new_w && fh == g.new_h) {                // LetterBox skips cv2.resize: identity taps
+            for (int d = 0; d < g.new_w; ++d) { xi[d] = d; a0[d] = 2048; a1[d] = 0; }
+            for (int d = 0; d < g.new_h; ++d) { i0[d] = d; i1[d] = d; b0[d] = 2048; b1[d] = 0; }
+        } else {
+            vti_plan_resize_taps_x(fw, g.new_w, xi.data(), a0.data(), a1.data());
+            vti_plan_resize_taps_y(fh, g.new_h, i0.data(), i1.data(), b0.data(), b1.data());
+        }
+        for (int d = 0; d < g.new_w; ++d) { xa[2 * d] = a0[d]; xa[2 * d + 1] = a1[d]; }
+        for (int d = 0; d < g.new_h; ++d) { yi[2 * d] = i0[d]; yi[2 * d + 1] = i1[d]; yb[2 * d] = b0[d]; yb[2 * d + 1] = b1[d]; }
+    }
+    if ((rc = upload(&h->d_tap_x_idx, xi)) || (rc = upload(&h->d_tap_x_a, xa)) || (rc = upload(&h->d_tap_y_i, yi)) ||
+        (rc = upload(&h->d_tap_y_b, yb))) { vti_destroy(h); return rc; }
+    if (p->undistort) {
+        std::vector<int32_t> ix((size_t)fh * fw), iy((size_t)fh * fw), packed((size_t)fh * fw);
+        vti_plan_undistort_map(p->K, p->dist, fh, fw, ix.data(), iy.data());
+        for (int v = 0; v < fh; ++v)
+            for (int u = 0; u < fw; ++u) {
+                const size_t i = (size_t)v * fw + u;
+                const int dx = ix[i] - 32 * u, dy = iy[i] - 32 * v;
+                if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) {
+                    vti_set_error("vti_create: lens displacement exceeds +-1024 px, unsupported");
+                    vti_destroy(h);
+                    return VTI_EINVAL;
+                }
+                packed[i] = (int32_t)(((uint32_t)(uint16_t)(int16_t)dy << 16) | (uint32_t)(uint16_t)(int16_t)dx);
+            }
+        if ((rc = upload(&h->d_und_lut, packed))) { vti_destroy(h); return rc; }
+    }
+    // ---- measurement tables
+    if ((rc = build_axis_lut(fh, g.LH, &h->lutY, nullptr)) || (rc = build_axis_lut(fw, g.LW, &h->lutX, &h->d_xmap))) {
+        vti_destroy(h);
+        return rc;
+    }
+    // ---- post scratch
+    const size_t B = p->max_batch;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+    alloc((void**)&h->d_cand_count, sizeof(int32_t) * B);
+    alloc((void**)&h->d_cand_key, sizeof(unsigned long long) * B * g.max_candidates);
+    alloc((void**)&h->d_cand_box, sizeof(float4) * B * g.A);
+    alloc((void**)&h->d_det_coef, sizeof(float) * B * p->max_det * VTI_NM);
+    alloc((void**)&h->d_env, sizeof(int32_t) * B * g.LW);
+    alloc((void**)&h->d_env_frame, sizeof(int32_t) * B * fw);
+    alloc((void**)&h->d_flags, sizeof(int32_t) * B);
+    if (e != cudaSuccess) {
+        vti_set_error(std::string("vti_create: cudaMalloc: ") + cudaGetErrorString(e));
+        vti_destroy(h);
+        return VTI_ENOMEM;
+    }
+    if ((rc = vti_k3_prepare(g.max_candidates))) { vti_destroy(h); return rc; }
+    *out = h;
+    return VTI_OK;
+}
+
+extern "C" int vti_get_geometry(const vti_handle* h, vti_geometry* out) {
+    if (!h || !out) return VTI_EINVAL;
+    *out = h->g;
+    return VTI_OK;
+}
+
+extern "C" int64_t vti_launch_count(const vti_handle* h) { return h ? h->launches : 0; }
+
+static int check_batch(const vti_handle* h, int B) {
+    if (!h || B < 1 || B > h->p.max_batch) {
+        vti_set_error("batch size out of range for this handle (max_batch)");
+        return VTI_EINVAL;
+    }
+    return VTI_OK;
+}
+
+extern "C" int vti_preprocess(vti_handle* h, const uint8_t* frames, int B, float* net_in, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!frames || !net_in) { vti_set_error("vti_preprocess: null buffer"); return VTI_EINVAL; }
+    return vti_launch_k1(h, frames, B, net_in, (cudaStream_t)stream);
+}
+
+extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, const float* p5, const float* coef,
+                               const float* proto, int B, vti_det* dets, int32_t* counts, uint32_t* masks,
+                               void* stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!p3 || !p4 || !p5 || !coef || !proto || !dets || !counts) {
+        vti_set_error("vti_postprocess: null buffer");
+        return VTI_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = vti_launch_k2(h, p3, p4, p5, B, s))) return rc;
+    if ((rc = vti_launch_k3(h, coef, B, dets, counts, s))) return rc;
+    return vti_launch_k4(h, proto, B, dets, counts, masks, s);
+}
+
+extern "C" int vti_measure(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* results,
+                           void* stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!dets || !counts || !results) { vti_set_error("vti_measure: null buffer"); return VTI_EINVAL; }
+    return vti_launch_k5(h, B, dets, counts, results, (cudaStream_t)stream);
+}
+
+extern "C" int vti_post_measure(vti_handle* h, const float* p3, const float* p4, const float* p5, const float* coef,
+                                const float* proto, int B, vti_det* dets, int32_t* counts, uint32_t* masks,
+                                vti_frame_result* results, void* stream) {
+    int rc = vti_postprocess(h, p3, p4, p5, coef, proto, B, dets, counts, masks, stream);
+    if (rc) return rc;
+    return vti_measure(h, B, dets, counts, results, stream);
+}
+
+static int ensure_staging(vti_handle* h) {
+    if (h->staged_batch) return VTI_OK;
+    const vti_geometry& g = h->g;
+    const size_t B = h->p.max_batch;
+    VTI_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    VTI_CUDA(cudaMalloc((void**)&h->d_frames, B * h->p.frame_h * h->p.frame_w * 3));
+    VTI_CUDA(cudaMalloc((void**)&h->d_net_in, sizeof(float) * B * 3 * g.LH * g.LW));
+    for (int l = 0; l < 3; ++l)
+        VTI_CUDA(cudaMalloc((void**)&h->d_p[l], sizeof(float) * B * (64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l]));
+    VTI_CUDA(cudaMalloc((void**)&h->d_coef, sizeof(float) * B * VTI_NM * g.A));
+    VTI_CUDA(cudaMalloc((void**)&h->d_proto, sizeof(float) * B * VTI_NM * g.ph * g.pw));
+    VTI_CUDA(cudaMalloc((void**)&h->d_dets, sizeof(vti_det) * B * h->p.max_det));
+    VTI_CUDA(cudaMalloc((void**)&h->d_counts, sizeof(int32_t) * B));
+    VTI_CUDA(cudaMalloc((void**)&h->d_results, sizeof(vti_frame_result) * B));
+    h->staged_batch = B;
+    return VTI_OK;
+}
+
+extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, const float* p4, const float* p5,
+                                const float* coef, const float* proto, int B, float* net_in, vti_det* dets,
+                                int32_t* counts, vti_frame_result* results) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!frames || !p3 || !p4 || !p5 || !coef || !proto || !dets || !counts || !results) {
+        vti_set_error("vti_process_host: null buffer");
+        return VTI_EINVAL;
+    }
+    if ((rc = ensure_staging(h))) return rc;
+    const vti_geometry& g = h->g;
+    cudaStream_t s = h->own_stream;
+    const float* hp[3] = {p3, p4, p5};
+    const size_t nb = (size_t)B;
+    VTI_CUDA(cudaMemcpyAsync(h->d_frames, frames, nb * h->p.frame_h * h->p.frame_w * 3, cudaMemcpyHostToDevice, s));
+    if ((rc = vti_launch_k1(h, h->d_frames, B, h->d_net_in, s))) return rc;
+    for (int l = 0; l < 3; ++l)
+        VTI_CUDA(cudaMemcpyAsync(h->d_p[l], hp[l], sizeof(float) * nb * (64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l],
+                                 cudaMemcpyHostToDevice, s));
+    VTI_CUDA(cudaMemcpyAsync(h->d_coef, coef, sizeof(float) * nb * VTI_NM * g.A, cudaMemcpyHostToDevice, s));
+    VTI_CUDA(cudaMemcpyAsync(h->d_proto, proto, sizeof(float) * nb * VTI_NM * g.ph * g.pw, cudaMemcpyHostToDevice, s));
+    if ((rc = vti_launch_k2(h, h->d_p[0], h->d_p[1], h->d_p[2], B, s))) return rc;
+    if ((rc = vti_launch_k3(h, h->d_coef, B, h->d_dets, h->d_counts, s))) return rc;
+    if ((rc = vti_launch_k4(h, h->d_proto, B, h->d_dets, h->d_counts, nullptr, s))) return rc;
+    if ((rc = vti_launch_k5(h, B, h->d_dets, h->d_counts, h->d_results, s))) return rc;
+    if (net_in)
+        VTI_CUDA(cudaMemcpyAsync(net_in, h->d_net_in, sizeof(float) * nb * 3 * g.LH * g.LW, cudaMemcpyDeviceToHost, s));
+    VTI_CUDA(cudaMemcpyAsync(dets, h->d_dets, sizeof(vti_det) * nb * h->p.max_det, cudaMemcpyDeviceToHost, s));
+    VTI_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    VTI_CUDA(cudaMemcpyAsync(results, h->d_results, sizeof(vti_frame_result) * nb, cudaMemcpyDeviceToHost, s));
+    VTI_CUDA(cudaStreamSynchronize(s));
+    return VTI_OK;
+}

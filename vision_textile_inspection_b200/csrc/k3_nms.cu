@@ -1,0 +1,267 @@
+// K3 -- class-offset greedy NMS with torchvision.ops.nms semantics, block-wide, one CTA per frame, followed by the
+// scale_boxes / clip / int() / ROI epilogue and the coefficient gather for the kept detections.
+//
+// Replaces (SURVEY.md 8a U4, U5, U7 and the box half of M1): ops.non_max_suppression + torchvision.ops.nms +
+// ops.scale_boxes (reached from /root/reference/measurement.py:208-210) and measurement.py:251-260.
+// Spec: oracle/post_spec.py nms_spec / scale_boxes_spec (bit-identical: same fp32 op order, no FMA, IoU compared
+// against the threshold in double exactly like the C++ kernel's `ovr > iou_threshold`).
+//
+//   1. bitonic sort of the 64-bit keys (score bits | ~anchor | cls) in shared memory, descending
+//      == stable descending score sort over ascending anchor order
+//   2. greedy sweep in chunks of 64 sorted candidates:
+//        a. every (candidate, already-kept box) pair is tested in parallel           -> suppressed-by-earlier bits
+//        b. the 64x64 intra-chunk IoU bitmask is built with one ballot per row half  -> row masks
+//        c. one warp resolves the chunk sequentially on register bitmasks            -> keep bits
+//      stops as soon as max_det boxes are kept ( == torchvision nms followed by [:max_det] )
+//   3. epilogue: un-letterbox + clip, int() truncation, ROI test on the truncated centre, class routing flags,
+//      gather of the 32 mask coefficients of each kept anchor into a compact [max_det][32] block for K4.
+#include <climits>
+
+#include "vti_internal.h"
+
+namespace {
+
+constexpr int K3_THREADS = 1024;
+constexpr int CHUNK = 64;
+constexpr int MAX_DET_CAP = 1024;
+
+struct K3Args {
+    const int32_t* cand_count;
+    unsigned long long* cand_key;
+    const float4* cand_box;
+    const float* coef;          // [B][32][A]
+    vti_det* dets;              // [B][max_det]
+    int32_t* counts;            // [B]
+    float* det_coef;            // [B][max_det][32]
+    int32_t* env;               // [B][LW]
+    int32_t* flags;             // [B] : bit0 overflow, bits 8.. = n_cand
+    int cap, A, max_det, LW;
+    double iou;
+    float gain, padx, pady, fw, fh;
+    int roi_active, rx1, ry1, rx2, ry2;
+    int stitch_id, fabric_id;
+    int env_init;
+};
+
+__device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4 b, float barea, double thr) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+    const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+    return (double)ovr > thr;
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    __shared__ float4 s_kbox[MAX_DET_CAP];      // kept boxes (class offset applied)
+    __shared__ float s_karea[MAX_DET_CAP];
+    __shared__ int s_kidx[MAX_DET_CAP];         // sorted position of each kept box
+    __shared__ float4 s_cbox[CHUNK];
+    __shared__ float s_carea[CHUNK];
+    __shared__ int s_sup[CHUNK];
+    __shared__ unsigned long long s_row[CHUNK];
+    __shared__ int s_nk;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n = a.cand_count[b];
+    const bool overflow = n > a.cap;
+    n = min(n, a.cap);
+    int n_pad = 64;
+    while (n_pad < n) n_pad <<= 1;
+
+    const unsigned long long* __restrict__ gkeys = a.cand_key + (size_t)b * a.cap;
+    for (int i = tid; i < n_pad; i += K3_THREADS) s_keys[i] = (i < n) ? gkeys[i] : 0ull;
+    for (int i = tid; i < a.LW; i += K3_THREADS) a.env[(size_t)b * a.LW + i] = a.env_init;
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+
+    // ---- 1. bitonic sort, descending
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pad; i += K3_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = s_keys[i], y = s_keys[p];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { s_keys[i] = y; s_keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 2. greedy sweep
+    const float4* __restrict__ gbox = a.cand_box + (size_t)b * a.A;
+    int nk = 0;
+    for (int c0 = 0; c0 < n && nk < a.max_det; c0 += CHUNK) {
+        if (tid < CHUNK) {
+            const int i = c0 + tid;
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            float ar = 0.f;
+            if (i < n) {
+                const unsigned long long key = s_keys[i];
+                const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
+                const float off = __fmul_rn((float)(int)(key & 0xFFull), 7680.0f);
+                const float4 r = gbox[anchor];
+                bx = make_float4(__fadd_rn(r.x, off), __fadd_rn(r.y, off), __fadd_rn(r.z, off), __fadd_rn(r.w, off));
+                ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+            }
+            s_cbox[tid] = bx;
+            s_carea[tid] = ar;
+            s_sup[tid] = (i < n) ? 0 : 1;
+        }
+        __syncthreads();
+        // a. against every box kept in earlier chunks
+        {
+            const int j = tid & (CHUNK - 1);
+            const float4 cb = s_cbox[j];
+            const float ca = s_carea[j];
+            bool sup = false;
+            for (int k = tid >> 6; k < nk; k += K3_THREADS / CHUNK) sup |= iou_gt(s_kbox[k], s_karea[k], cb, ca, a.iou);
+            if (sup) s_sup[j] = 1;
+        }
+        // b. intra-chunk rows: warp w builds rows w and w+32; bit k of row j = IoU(j,k) > thr, k > j only
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int j = warp + 32 * half;
+            const float4 jb = s_cbox[j];
+            const float ja = s_carea[j];
+            const bool lo = (lane > j) && iou_gt(jb, ja, s_cbox[lane], s_carea[lane], a.iou);
+            const bool hi = (lane + 32 > j) && iou_gt(jb, ja, s_cbox[lane + 32], s_carea[lane + 32], a.iou);
+            const unsigned mlo = __ballot_sync(0xffffffffu, lo), mhi = __ballot_sync(0xffffffffu, hi);
+            if (lane == 0) s_row[j] = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+        }
+        __syncthreads();
+        // c. sequential resolve on one warp (all lanes redundantly; the row loads do not depend on the chain)
+        if (warp == 0) {
+            const unsigned slo = __ballot_sync(0xffffffffu, s_sup[lane] != 0);
+            const unsigned shi = __ballot_sync(0xffffffffu, s_sup[lane + 32] != 0);
+            unsigned long long removed = (unsigned long long)slo | ((unsigned long long)shi << 32);
+            unsigned long long keep = 0ull;
+            int room = a.max_det - nk;
+#pragma unroll 8
+            for (int i = 0; i < CHUNK; ++i) {
+                const unsigned long long row = s_row[i];
+                const bool k = (((removed >> i) & 1ull) == 0ull) && (room > 0);
+                if (k) { keep |= (1ull << i); removed |= row; --room; }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = lane + 32 * half;
+                if ((keep >> i) & 1ull) {
+                    const int pos = nk + __popcll(keep & ((1ull << i) - 1ull));
+                    s_kbox[pos] = s_cbox[i];
+                    s_karea[pos] = s_carea[i];
+                    s_kidx[pos] = c0 + i;
+                }
+            }
+            if (lane == 0) s_nk = nk + __popcll(keep);
+        }
+        __syncthreads();
+        nk = s_nk;
+    }
+
+    // ---- 3. epilogue
+    vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
+    if (tid < nk) {
+        const unsigned long long key = s_keys[s_kidx[tid]];
+        const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
+        const int cls = (int)(key & 0xFFull);
+        const float4 r = gbox[anchor];
+        vti_det d;
+        d.box_lb[0] = r.x; d.box_lb[1] = r.y; d.box_lb[2] = r.z; d.box_lb[3] = r.w;
+        const float fx1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r.x, a.padx), a.gain), 0.0f), a.fw);
+        const float fy1 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r.y, a.pady), a.gain), 0.0f), a.fh);
+        const float fx2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r.z, a.padx), a.gain), 0.0f), a.fw);
+        const float fy2 = fminf(fmaxf(__fdiv_rn(__fsub_rn(r.w, a.pady), a.gain), 0.0f), a.fh);
+        d.box_frame[0] = fx1; d.box_frame[1] = fy1; d.box_frame[2] = fx2; d.box_frame[3] = fy2;
+        const int x1 = (int)fx1, y1 = (int)fy1, x2 = (int)fx2, y2 = (int)fy2;
+        d.box_int[0] = x1; d.box_int[1] = y1; d.box_int[2] = x2; d.box_int[3] = y2;
+        d.conf = __uint_as_float((unsigned)(key >> 32));
+        d.cls = cls;
+        d.anchor = anchor;
+        unsigned f = 0;
+        bool in_roi = true;
+        if (a.roi_active) {
+            const int sx = x1 + x2, sy = y1 + y2;    // 0.5*(x1+x2) in [rx1, rx2]  <=>  x1+x2 in [2 rx1, 2 rx2]
+            in_roi = (2 * a.rx1 <= sx) && (sx <= 2 * a.rx2) && (2 * a.ry1 <= sy) && (sy <= 2 * a.ry2);
+        }
+        if (in_roi) f |= VTI_F_IN_ROI;
+        if (cls == a.stitch_id) f |= VTI_F_STITCH;
+        else if (cls == a.fabric_id) f |= VTI_F_FABRIC;
+        d.flags = f;
+        d.m00 = 0; d.m10 = 0; d.m01 = 0;
+        d.col_min = INT_MAX; d.col_max = -1;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        d.cx = qnan; d.cy = qnan; d.left_px = qnan; d.right_px = qnan;
+        d.width_mm = qnan; d.edge_y = qnan; d.dist_mm = qnan; d.reserved = 0.0;
+        dets[tid] = d;
+    }
+    // coefficient gather: [32][A] strided -> compact [nk][32]
+    const float* __restrict__ coef = a.coef + (size_t)b * VTI_NM * a.A;
+    float* __restrict__ dc = a.det_coef + (size_t)b * a.max_det * VTI_NM;
+    for (int i = tid; i < nk * VTI_NM; i += K3_THREADS) {
+        const int k = i >> 5, c = i & 31;
+        const unsigned long long key = s_keys[s_kidx[k]];
+        const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
+        dc[i] = __ldg(coef + (size_t)c * a.A + anchor);
+    }
+    if (tid == 0) {
+        a.counts[b] = nk;
+        a.flags[b] = (overflow ? 1 : 0) | (n << 8);
+    }
+}
+
+}  // namespace
+
+size_t vti_k3_smem_bytes(int cap) {
+    int n_pad = 64;
+    while (n_pad < cap) n_pad <<= 1;
+    return (size_t)n_pad * sizeof(unsigned long long);
+}
+
+int vti_k3_prepare(int cap) {
+    VTI_CUDA(cudaFuncSetAttribute(k3_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)vti_k3_smem_bytes(cap)));
+    return VTI_OK;
+}
+
+int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, cudaStream_t s) {
+    K3Args a;
+    a.cand_count = h->d_cand_count;
+    a.cand_key = h->d_cand_key;
+    a.cand_box = h->d_cand_box;
+    a.coef = coef;
+    a.dets = dets;
+    a.counts = counts;
+    a.det_coef = h->d_det_coef;
+    a.env = h->d_env;
+    a.flags = h->d_flags;
+    a.cap = h->g.max_candidates; a.A = h->g.A; a.max_det = h->p.max_det; a.LW = h->g.LW;
+    a.iou = (double)h->p.iou;
+    const int fh = h->p.frame_h, fw = h->p.frame_w, LH = h->g.LH, LW = h->g.LW;
+    // ops.scale_boxes: gain/pad are Python doubles, the tensor math is float32 (oracle/post_spec.py scale_boxes_spec)
+    const double g1 = (double)LH / fh, g2 = (double)LW / fw;
+    const double gain = g1 < g2 ? g1 : g2;
+    a.gain = (float)gain;
+    a.padx = (float)nearbyint((LW - fw * gain) / 2 - 0.1);
+    a.pady = (float)nearbyint((LH - fh * gain) / 2 - 0.1);
+    a.fw = (float)fw; a.fh = (float)fh;
+    a.roi_active = 0; a.rx1 = a.ry1 = a.rx2 = a.ry2 = 0;
+    if (h->p.variant == 0 && h->p.roi_enabled) {        // measurement.py:220-238
+        auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+        const int x_min = clampi(h->p.roi_x_min, 0, fw - 1), x_max = clampi(h->p.roi_x_max, 0, fw - 1);
+        const int y_min = clampi(h->p.roi_y_min, 0, fh - 1), y_max = clampi(h->p.roi_y_max, 0, fh - 1);
+        if (x_min < x_max && y_min < y_max) {
+            a.roi_active = 1; a.rx1 = x_min; a.ry1 = y_min; a.rx2 = x_max; a.ry2 = y_max;
+        }
+    }
+    a.stitch_id = h->p.stitch_id; a.fabric_id = h->p.fabric_id;
+    a.env_init = (h->p.variant == 1) ? INT_MAX : -1;
+    k3_nms_kernel<<<B, K3_THREADS, vti_k3_smem_bytes(h->g.max_candidates), s>>>(a);
+    h->launches++;
+    VTI_CUDA(cudaGetLastError());
+    return VTI_OK;
+}

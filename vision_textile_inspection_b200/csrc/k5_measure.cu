@@ -1,0 +1,389 @@
+// K5 -- the measure stage on the per-detection statistics K4 produced: routing, frame-resolution envelope, centroids,
+// column extent, 1-D k-means row selection, envelope-proximity filter and the fp64 pixel -> millimetre projection.
+//
+// Replaces (all fp64, exactly the reference's decisions):
+//   /root/reference/measurement.py:44-65    compute_camera_plane / pixel_to_world_using_camera_plane
+//                                           (cv2.undistortPoints == exactly 5 fixed-point iterations, (u-cx)*(1/fx))
+//   /root/reference/measurement.py:88-113   kmeans_1d_two_clusters (labels NOT updated on break)
+//   /root/reference/measurement.py:280-289, 302-330, 343-356, 390-430, 440-472
+//   variant 1: /root/reference/Utils/check_stitch_distance.py:143-171 (labels updated on break), :331-334 (bbox-filled
+//              fabric fallback), :349 (upper envelope), :442-443 (0 < d < 150), :489-507 (widths of final stitches only)
+// Spec / oracle: oracle/measure_port.py (pinned against the verbatim reference through tests/golden/).
+//
+// One CTA per frame.  Per-stitch work is thread-parallel; the order-dependent pieces (k-means, numpy's pairwise
+// summation order for np.mean, ordered list building) run on thread 0 so that results follow the reference's
+// floating-point evaluation order.  Compiled with --fmad=false: numpy / OpenCV do not fuse multiply-adds.
+// The 8-frame temporal median (measurement.py:474-484) is frame-ordered state and stays on the host.
+#include <climits>
+
+#include "vti_internal.h"
+
+namespace {
+
+constexpr int K5_THREADS = 256;
+constexpr int MAXN = 1024;
+
+struct Camera {
+    double fx, fy, cx, cy, ifx, ify;
+    double k1, k2, p1, p2, k3;
+    double R[9], t[3], n[3], d_c;
+};
+
+struct K5Args {
+    vti_det* dets;
+    const int32_t* counts;
+    const int32_t* env;        // [B][LW]
+    int32_t* env_frame;        // [B][w]
+    const int32_t* xmap;       // [w]
+    const int32_t* flags;
+    vti_frame_result* res;
+    Camera cam;
+    int max_det, LW, w, h;
+    int variant, min_stitches, max_px, nb;
+};
+
+__device__ __forceinline__ bool pixel_to_world(const Camera& c, double u, double v, double out[3]) {
+    const double x0 = (u - c.cx) * c.ifx, y0 = (v - c.cy) * c.ify;
+    double x = x0, y = y0;
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = x * x + y * y;
+        const double icd = 1.0 / (1.0 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+        const double dx = 2.0 * c.p1 * x * y + c.p2 * (r2 + 2.0 * x * x);
+        const double dy = c.p1 * (r2 + 2.0 * y * y) + 2.0 * c.p2 * x * y;
+        x = (x0 - dx) * icd;
+        y = (y0 - dy) * icd;
+    }
+    const double den = c.n[0] * x + c.n[1] * y + c.n[2];
+    if (fabs(den) < 1e-9) return false;
+    const double s = -c.d_c / den;
+    const double v0 = s * x - c.t[0], v1 = s * y - c.t[1], v2 = s - c.t[2];
+    out[0] = c.R[0] * v0 + c.R[3] * v1 + c.R[6] * v2;
+    out[1] = c.R[1] * v0 + c.R[4] * v1 + c.R[7] * v2;
+    out[2] = c.R[2] * v0 + c.R[5] * v1 + c.R[8] * v2;
+    return true;
+}
+
+__device__ __forceinline__ bool dist_mm(const Camera& c, double u0, double v0, double u1, double v1, double* mm) {
+    double a[3], b[3];
+    if (!pixel_to_world(c, u0, v0, a) || !pixel_to_world(c, u1, v1, b)) return false;
+    const double d0 = b[0] - a[0], d1 = b[1] - a[1], d2 = b[2] - a[2];
+    *mm = sqrt(d0 * d0 + d1 * d1 + d2 * d2) * 1000.0;
+    return true;
+}
+
+// numpy's pairwise summation (add.reduce on a contiguous float64 vector) -- same association order
+__device__ double np_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_sum(a, n2) + np_sum(a + n2, n - n2);
+}
+
+// median of the valid envelope rows at columns clip(cx_int + dx, 0, w-1), dx in [-nb, nb]; false if none valid
+__device__ __forceinline__ bool env_median(const int32_t* envf, int w, int cx_int, int nb, double* med) {
+    int v[16];
+    int m = 0;
+    for (int dx = -nb; dx <= nb; ++dx) {
+        const int x = min(max(cx_int + dx, 0), w - 1);
+        const int e = envf[x];
+        if (e >= 0) {
+            int j = m++;
+            while (j > 0 && v[j - 1] > e) { v[j] = v[j - 1]; --j; }
+            v[j] = e;
+        }
+    }
+    if (m == 0) return false;
+    *med = (m & 1) ? (double)v[m >> 1] : ((double)v[(m >> 1) - 1] + (double)v[m >> 1]) / 2.0;
+    return true;
+}
+
+__global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) {
+    __shared__ double s_cy[MAXN];
+    __shared__ double s_tmp[MAXN];
+    __shared__ short s_st[MAXN];          // stitch list -> det index
+    __shared__ short s_sel[MAXN];         // selected -> stitch index
+    __shared__ short s_fin[MAXN];
+    __shared__ unsigned char s_lab[MAXN], s_new[MAXN], s_pass[MAXN];
+    __shared__ int s_ns, s_nsel, s_nfin, s_nfab;
+    __shared__ long long s_envsum;
+    __shared__ int s_envcnt;
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = a.counts[b];
+    vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
+    int32_t* __restrict__ envf = a.env_frame + (size_t)b * a.w;
+    const Camera& cam = a.cam;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    if (tid == 0) { s_envsum = 0; s_envcnt = 0; s_nfab = 0; }
+    // ---- finalize K4's statistics, frame-resolution envelope
+    for (int k = tid; k < n; k += K5_THREADS) {
+        if (dets[k].m00 > 0) dets[k].flags |= VTI_F_HAS_MASK;
+        else { dets[k].col_min = -1; dets[k].col_max = -1; }
+    }
+    const int* __restrict__ env = a.env + (size_t)b * a.LW;
+    for (int x = tid; x < a.w; x += K5_THREADS) {
+        int e = env[a.xmap[x]];
+        envf[x] = e;                       // variant 1 keeps INT_MAX = none until the rectangles are merged
+    }
+    __syncthreads();
+    if (a.variant == 1) {
+        // mask-less fabric detection -> filled bbox rectangle (check_stitch_distance.py:331-334), upper envelope
+        for (int k = 0; k < n; ++k) {
+            const unsigned f = dets[k].flags;
+            if (!(f & VTI_F_FABRIC) || (f & VTI_F_HAS_MASK)) continue;
+            const int x1 = max(min(dets[k].box_int[0], dets[k].box_int[2]), 0);
+            const int x2 = min(max(dets[k].box_int[0], dets[k].box_int[2]), a.w - 1);
+            const int y1 = max(min(dets[k].box_int[1], dets[k].box_int[3]), 0);
+            const int y2 = min(max(dets[k].box_int[1], dets[k].box_int[3]), a.h - 1);
+            if (y1 > y2) continue;
+            for (int x = x1 + tid; x <= x2; x += K5_THREADS) envf[x] = min(envf[x], y1);
+            __syncthreads();               // uniform: n and the flags are the same for every thread
+        }
+        __syncthreads();
+        for (int x = tid; x < a.w; x += K5_THREADS)
+            if (envf[x] == INT_MAX) envf[x] = -1;
+        __syncthreads();
+    }
+    {
+        long long sum = 0;
+        int cnt = 0;
+        for (int x = tid; x < a.w; x += K5_THREADS) {
+            const int e = envf[x];
+            if (e >= 0) { sum += e; ++cnt; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if ((tid & 31) == 0 && cnt > 0) {
+            atomicAdd((unsigned long long*)&s_envsum, (unsigned long long)sum);
+            atomicAdd(&s_envcnt, cnt);
+        }
+    }
+    // ---- routing (measurement.py:249-272): ordered stitch list
+    if (tid == 0) {
+        int ns = 0, nf = 0;
+        for (int k = 0; k < n; ++k) {
+            const unsigned f = dets[k].flags;
+            if (!(f & VTI_F_IN_ROI)) continue;
+            if (f & VTI_F_STITCH) s_st[ns++] = (short)k;
+            else if ((f & VTI_F_FABRIC) && ((f & VTI_F_HAS_MASK) || a.variant == 1)) ++nf;
+        }
+        s_ns = ns;
+        s_nfab = nf;
+    }
+    __syncthreads();
+    const int ns = s_ns;
+    vti_frame_result r;
+    r.status = VTI_ST_OK;
+    r.n_det = n;
+    r.n_cand = a.flags[b] >> 8;
+    r.n_stitch = ns;
+    r.n_fabric = s_nfab;
+    r.n_dist = 0; r.n_width = 0;
+    r.env_valid = s_envcnt;
+    r.avg_dist = qnan; r.avg_width = qnan;
+    r.env_mean = s_envcnt > 0 ? (double)s_envsum / (double)s_envcnt : qnan;
+    const int ovf = (a.flags[b] & 1) ? VTI_ST_OVERFLOW : 0;
+    if (s_envcnt == 0 || ns == 0) {
+        if (tid == 0) {
+            r.status = (s_envcnt == 0 ? VTI_ST_NO_FABRIC : VTI_ST_NO_STITCH) | ovf;
+            a.res[b] = r;
+        }
+        return;
+    }
+
+    // ---- per-stitch centroid / extent (measurement.py:302-330) and, variant 0, width of every stitch (:343-356)
+    for (int i = tid; i < ns; i += K5_THREADS) {
+        vti_det& d = dets[s_st[i]];
+        double cx, cy, left, right;
+        const int x1 = d.box_int[0], y1 = d.box_int[1], x2 = d.box_int[2], y2 = d.box_int[3];
+        if (d.m00 > 0) {
+            cx = (double)d.m10 / (double)d.m00;
+            cy = (double)d.m01 / (double)d.m00;
+            left = (double)d.col_min;
+            right = (double)d.col_max;
+        } else {
+            cx = (double)(x1 + x2) / 2.0;
+            cy = (double)(y1 + y2) / 2.0;
+            left = (double)x1;
+            right = (double)x2;
+        }
+        d.cx = cx; d.cy = cy; d.left_px = left; d.right_px = right;
+        s_cy[i] = cy;
+        if (a.variant == 0) {
+            double mm;
+            if (dist_mm(cam, left, cy, right, cy, &mm)) { d.width_mm = mm; d.flags |= VTI_F_HAS_WIDTH; }
+        }
+    }
+    __syncthreads();
+
+    // ---- row selection (measurement.py:390-406)
+    if (tid == 0) {
+        int nsel = 0;
+        if (ns >= 2) {
+            double c0 = s_cy[0], c1 = s_cy[0];
+            for (int i = 1; i < ns; ++i) { c0 = fmin(c0, s_cy[i]); c1 = fmax(c1, s_cy[i]); }
+            for (int i = 0; i < ns; ++i) s_lab[i] = 0;
+            for (int it = 0; it < 10; ++it) {
+                int ones = 0;
+                for (int i = 0; i < ns; ++i) {
+                    s_new[i] = fabs(s_cy[i] - c1) < fabs(s_cy[i] - c0);
+                    ones += s_new[i];
+                }
+                if (ones == 0 || ones == ns) {
+                    if (a.variant == 1) for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
+                    break;
+                }
+                int m = 0;
+                for (int i = 0; i < ns; ++i) if (!s_new[i]) s_tmp[m++] = s_cy[i];
+                const double n0 = np_sum(s_tmp, m) / (double)m;
+                m = 0;
+                for (int i = 0; i < ns; ++i) if (s_new[i]) s_tmp[m++] = s_cy[i];
+                const double n1 = np_sum(s_tmp, m) / (double)m;
+                if (n0 == c0 && n1 == c1) {
+                    if (a.variant == 1) for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
+                    break;
+                }
+                c0 = n0; c1 = n1;
+                for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
+            }
+            int chosen = 0;
+            {
+                const double fm = (double)s_envsum / (double)s_envcnt;
+                double m0 = 1e9, m1 = 1e9;
+                int m = 0;
+                for (int i = 0; i < ns; ++i) if (s_lab[i] == 0) s_tmp[m++] = s_cy[i];
+                if (m > 0) m0 = np_sum(s_tmp, m) / (double)m;
+                m = 0;
+                for (int i = 0; i < ns; ++i) if (s_lab[i] == 1) s_tmp[m++] = s_cy[i];
+                if (m > 0) m1 = np_sum(s_tmp, m) / (double)m;
+                chosen = (fabs(m0 - fm) < fabs(m1 - fm)) ? 0 : 1;
+            }
+            for (int i = 0; i < ns; ++i) if (s_lab[i] == chosen) s_sel[nsel++] = (short)i;
+        } else {
+            for (int i = 0; i < ns; ++i) s_sel[nsel++] = (short)i;
+        }
+        s_nsel = nsel;
+    }
+    __syncthreads();
+    const int nsel = s_nsel;
+
+    // ---- envelope-proximity filter (measurement.py:409-430)
+    for (int j = tid; j < nsel; j += K5_THREADS) {
+        const vti_det& d = dets[s_st[s_sel[j]]];
+        const int cxr = (int)rint(d.cx);
+        double med;
+        bool ok = false;
+        if (env_median(envf, a.w, cxr, a.nb, &med)) {
+            const double env_y = (double)(int)rint(med);
+            const double dd = d.cy - env_y;
+            ok = (a.variant == 0) ? (fabs(dd) < (double)a.max_px) : (dd > 0.0 && dd < (double)a.max_px);
+        }
+        s_pass[j] = ok;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nf = 0;
+        for (int j = 0; j < nsel; ++j) if (s_pass[j]) s_fin[nf++] = s_sel[j];
+        if (nf == 0) { for (int j = 0; j < nsel; ++j) s_fin[j] = s_sel[j]; nf = nsel; }
+        s_nfin = nf;
+    }
+    __syncthreads();
+    const int nfin = s_nfin;
+    for (int j = tid; j < nsel; j += K5_THREADS) dets[s_st[s_sel[j]]].flags |= VTI_F_SELECTED;
+    __syncthreads();                       // the same record gets VTI_F_FINAL from a different thread below
+
+    // ---- edge distances (measurement.py:440-459) [+ widths of the final stitches, variant 1]
+    for (int j = tid; j < nfin; j += K5_THREADS) {
+        vti_det& d = dets[s_st[s_fin[j]]];
+        d.flags |= VTI_F_FINAL;
+        const int cx_int = min(max((int)rint(d.cx), 0), a.w - 1);
+        double med, mm;
+        if (env_median(envf, a.w, cx_int, a.nb, &med)) {
+            d.edge_y = med;
+            if (dist_mm(cam, d.cx, d.cy, d.cx, med, &mm)) { d.dist_mm = mm; d.flags |= VTI_F_HAS_DIST; }
+        }
+        if (a.variant == 1) {
+            if (dist_mm(cam, d.left_px, d.cy, d.right_px, d.cy, &mm)) {
+                d.width_mm = mm; d.flags |= VTI_F_HAS_WIDTH;
+            } else if (dist_mm(cam, d.cx, d.cy, d.cx + 10.0, d.cy, &mm)) {
+                d.width_mm = ((d.right_px - d.left_px) / 10.0) * mm; d.flags |= VTI_F_HAS_WIDTH;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- averages (measurement.py:469-472), numpy summation order
+    if (tid == 0) {
+        int m = 0;
+        for (int j = 0; j < nfin; ++j) {
+            const vti_det& d = dets[s_st[s_fin[j]]];
+            if (d.flags & VTI_F_HAS_DIST) s_tmp[m++] = d.dist_mm;
+        }
+        r.n_dist = m;
+        if (m >= a.min_stitches) r.avg_dist = np_sum(s_tmp, m) / (double)m;
+        m = 0;
+        if (a.variant == 0) {
+            for (int i = 0; i < ns; ++i) {
+                const vti_det& d = dets[s_st[i]];
+                if (d.flags & VTI_F_HAS_WIDTH) s_tmp[m++] = d.width_mm;
+            }
+        } else {
+            for (int j = 0; j < nfin; ++j) {
+                const vti_det& d = dets[s_st[s_fin[j]]];
+                if (d.flags & VTI_F_HAS_WIDTH) s_tmp[m++] = d.width_mm;
+            }
+        }
+        r.n_width = m;
+        if (m >= a.min_stitches) r.avg_width = np_sum(s_tmp, m) / (double)m;
+        r.status = VTI_ST_OK | ovf;
+        a.res[b] = r;
+    }
+}
+
+}  // namespace
+
+int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* res, cudaStream_t s) {
+    K5Args a;
+    a.dets = dets;
+    a.counts = counts;
+    a.env = h->d_env;
+    a.env_frame = h->d_env_frame;
+    a.xmap = h->d_xmap;
+    a.flags = h->d_flags;
+    a.res = res;
+    const vti_params& p = h->p;
+    Camera& c = a.cam;
+    c.fx = p.K[0]; c.fy = p.K[4]; c.cx = p.K[2]; c.cy = p.K[5];
+    c.ifx = 1.0 / c.fx; c.ify = 1.0 / c.fy;
+    const bool lens = !p.undistort;     // image already undistorted by K1 -> points are measured with dist = 0
+    c.k1 = lens ? p.dist[0] : 0.0; c.k2 = lens ? p.dist[1] : 0.0;
+    c.p1 = lens ? p.dist[2] : 0.0; c.p2 = lens ? p.dist[3] : 0.0; c.k3 = lens ? p.dist[4] : 0.0;
+    for (int i = 0; i < 9; ++i) c.R[i] = p.R[i];
+    for (int i = 0; i < 3; ++i) c.t[i] = p.t[i];
+    c.n[0] = p.R[2]; c.n[1] = p.R[5]; c.n[2] = p.R[8];                 // n_c = R[:, 2]   (measurement.py:46)
+    c.d_c = -(c.n[0] * p.t[0] + c.n[1] * p.t[1] + c.n[2] * p.t[2]);     // measurement.py:47
+    a.max_det = p.max_det; a.LW = h->g.LW; a.w = p.frame_w; a.h = p.frame_h;
+    a.variant = p.variant; a.min_stitches = p.min_stitches; a.max_px = p.max_px_distance; a.nb = p.neighborhood;
+    k5_measure_kernel<<<B, K5_THREADS, 0, s>>>(a);
+    h->launches++;
+    VTI_CUDA(cudaGetLastError());
+    return VTI_OK;
+}

@@ -1,0 +1,92 @@
+// Internal declarations shared by the kernels and the C-ABI glue of libvti.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vti.h"
+
+static_assert(sizeof(vti_det) == 160, "vti_det must stay 160 bytes");
+
+#define VTI_CAND_CAP_MAX 16384
+
+// Per-axis letterbox-pixel -> frame-pixel multiplicity tables of cv2.resize(INTER_NEAREST) (measurement.py:78-79).
+// A letterbox row Y is hit by cnt[Y] frame rows whose indices sum to sum[Y]; first/last are the extreme frame rows.
+struct AxisLut {
+    int32_t* cnt;
+    int32_t* sum;
+    int32_t* first;   // INT_MAX when cnt == 0
+    int32_t* last;    // -1 when cnt == 0
+};
+
+struct vti_handle {
+    vti_params p;
+    vti_geometry g;
+    int device;
+    int num_sms;
+    int64_t launches;
+
+    // ---- K1 tables (device)
+    int32_t* d_tap_x_idx;  int16_t* d_tap_x_a;    // [new_w], [new_w*2]
+    int32_t* d_tap_y_i;    int16_t* d_tap_y_b;    // [new_h*2], [new_h*2]
+    int32_t* d_und_lut;                            // [frame_h*frame_w] packed (dy16<<16 | dx16), undistort only
+    int resize_mode;                               // 0 copy, 1 bilinear, 2 exact-2x area
+    // ---- measurement tables (device)
+    AxisLut lutY, lutX;                            // [LH], [LW]
+    int32_t* d_xmap;                               // [frame_w] frame col -> letterbox col
+    // ---- post scratch (device), sized for max_batch
+    int32_t* d_cand_count;                         // [B]
+    unsigned long long* d_cand_key;                // [B][cap]
+    float4* d_cand_box;                            // [B][A]   xyxy by anchor
+    float* d_det_coef;                             // [B][max_det][32]
+    int32_t* d_env;                                // [B][LW]  envelope in frame rows at letterbox columns
+    int32_t* d_env_frame;                          // [B][frame_w]
+    int32_t* d_flags;                              // [B] overflow etc.
+    // ---- host-buffer path
+    cudaStream_t own_stream;
+    uint8_t* d_frames; float* d_net_in; float* d_p[3]; float* d_coef; float* d_proto;
+    vti_det* d_dets; int32_t* d_counts; vti_frame_result* d_results;
+    size_t staged_batch;
+};
+
+void vti_set_error(const std::string& s);
+#define VTI_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            vti_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+            return VTI_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+// kernel launchers (each returns VTI_OK / VTI_ECUDA)
+int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s);
+int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* p5, int B, cudaStream_t s);
+int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, cudaStream_t s);
+int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const int32_t* counts, uint32_t* masks,
+                  cudaStream_t s);
+int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* res, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- bit-reproducible float32 exp / sigmoid: mirrors oracle/post_spec.py exp_spec / sigmoid_spec op for op.
+__device__ __forceinline__ float vti_exp_spec(float x) {
+    x = fminf(fmaxf(x, -86.0f), 88.0f);
+    const float n = rintf(__fmul_rn(x, 1.4426950408889634f));
+    float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
+    r = __fsub_rn(r, __fmul_rn(n, -2.12194440e-4f));
+    float p = 1.0f / 5040.0f;
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 720.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 120.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 24.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 6.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 0.5f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f);
+    return __fmul_rn(p, __int_as_float(((int)n + 127) << 23));
+}
+__device__ __forceinline__ float vti_sigmoid_spec(float x) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, vti_exp_spec(-x)));
+}
+#endif

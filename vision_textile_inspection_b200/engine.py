@@ -1,0 +1,235 @@
+"""InspectionEngine -- host-side owner of one libvti handle on one GPU.
+
+PyTorch is plumbing here (device memory, streams); every stage runs in the hand-written kernels behind the C ABI
+(include/vti.h).  There is no CPU or eager-PyTorch fallback: without libvti.so or without a CUDA device the engine
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DET_DTYPE, RESULT_DTYPE, VtiGeometry, VtiParams, check
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def load_reference_calibration() -> dict:
+    """K / dist / rvec / tvec values of the reference's calibration JSONs (regenerated fixture, see oracle/gen_golden.py)."""
+    with open(os.path.join(DATA, "reference_calibration.json")) as f:
+        return json.load(f)
+
+
+def rodrigues(rvec) -> np.ndarray:
+    """Rotation vector -> matrix (same formula as cv2.Rodrigues; measurement.py:139)."""
+    r = np.asarray(rvec, np.float64).reshape(3)
+    th = float(np.linalg.norm(r))
+    if th < 1e-300:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(k, k) + np.sin(th) * Kx
+
+
+@dataclass
+class EngineConfig:
+    frame_h: int
+    frame_w: int
+    K: np.ndarray
+    dist: np.ndarray
+    R: np.ndarray
+    t: np.ndarray
+    imgsz: int = 960
+    stride: int = 32
+    nc: int = 2
+    conf: float = 0.20            # config.py:71
+    iou: float = 0.25             # config.py:72
+    max_det: int = 200            # config.py:73
+    max_batch: int = 1
+    variant: int = 0              # 0 measurement.py, 1 Utils/check_stitch_distance.py
+    undistort: int = 0
+    channel_flip: int = 0
+    stitch_id: int = 0
+    fabric_id: int = 1
+    roi: tuple = (1, 10, 1270, 300, 760)
+    min_stitches: int = 3
+    max_px_distance: int = 250
+    neighborhood: int = 3
+    max_candidates: int = 0
+
+    @staticmethod
+    def for_workload(cfg, calib: dict | None = None, max_batch: int | None = None) -> "EngineConfig":
+        """EngineConfig for a synth.WorkloadConfig: K scaled from the 1280x960 calibration size."""
+        calib = calib or load_reference_calibration()
+        K = np.diag([cfg.frame_w / 1280.0, cfg.frame_h / 960.0, 1.0]) @ np.array(calib["camera_matrix"], np.float64)
+        ex = calib[cfg.extrinsics]
+        try:
+            import cv2
+            R = cv2.Rodrigues(np.asarray(ex["rvec"], np.float64).reshape(3, 1))[0]
+        except Exception:  # pragma: no cover
+            R = rodrigues(ex["rvec"])
+        return EngineConfig(
+            frame_h=cfg.frame_h, frame_w=cfg.frame_w, K=K, dist=np.array(calib["dist_coeffs"], np.float64), R=R,
+            t=np.array(ex["tvec"], np.float64), imgsz=cfg.imgsz, nc=cfg.nc, conf=cfg.conf, iou=cfg.iou,
+            max_det=cfg.max_det, max_batch=max_batch or cfg.batch, variant=cfg.variant, undistort=cfg.undistort,
+            roi=cfg.roi(), max_px_distance=250 if cfg.variant == 0 else 150)
+
+    def to_params(self) -> VtiParams:
+        p = VtiParams()
+        p.struct_size = C.sizeof(VtiParams)
+        p.frame_h, p.frame_w, p.imgsz, p.stride = self.frame_h, self.frame_w, self.imgsz, self.stride
+        p.nc, p.max_det, p.max_batch = self.nc, self.max_det, self.max_batch
+        p.variant, p.undistort, p.channel_flip = self.variant, self.undistort, self.channel_flip
+        p.stitch_id, p.fabric_id = self.stitch_id, self.fabric_id
+        p.roi_enabled, p.roi_x_min, p.roi_x_max, p.roi_y_min, p.roi_y_max = [int(v) for v in self.roi]
+        p.min_stitches, p.max_px_distance, p.neighborhood = self.min_stitches, self.max_px_distance, self.neighborhood
+        p.max_candidates = self.max_candidates
+        p.conf, p.iou = self.conf, self.iou
+        p.K[:] = np.asarray(self.K, np.float64).reshape(9).tolist()
+        p.dist[:] = np.asarray(self.dist, np.float64).reshape(-1)[:5].tolist()
+        p.R[:] = np.asarray(self.R, np.float64).reshape(9).tolist()
+        p.t[:] = np.asarray(self.t, np.float64).reshape(3).tolist()
+        return p
+
+
+class InspectionEngine:
+    """One libvti handle bound to one CUDA device.  All tensor arguments are CUDA tensors on that device."""
+
+    def __init__(self, cfg: EngineConfig, device: int | str | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.VtiError("InspectionEngine needs a CUDA device: the hot path has no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _lib.VtiError("InspectionEngine device must be CUDA")
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_create(C.byref(cfg.to_params()), C.byref(self._h)), "vti_create")
+        g = VtiGeometry()
+        check(self.lib.vti_get_geometry(self._h, C.byref(g)), "vti_get_geometry")
+        self.g = g
+        self.LH, self.LW, self.ph, self.pw, self.A = g.LH, g.LW, g.ph, g.pw, g.A
+        self.level_shapes = [(g.lvl_h[i], g.lvl_w[i]) for i in range(3)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.vti_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t: torch.Tensor, dtype, shape, name):
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype} {tuple(shape)} on {self.device}, got "
+                             f"{t.dtype} {tuple(t.shape)} on {t.device}")
+
+    def alloc_outputs(self, B: int, masks: bool = False):
+        dets = torch.empty((B, self.cfg.max_det, DET_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        results = torch.empty((B, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        m = None
+        if masks:
+            m = torch.empty((B, self.cfg.max_det, self.LH, self.LW // 32), dtype=torch.int32, device=self.device)
+        return dets, counts, results, m
+
+    # ------------------------------------------------------------------------------------------------- stages
+    def preprocess(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """K1.  frames (B,h,w,3) uint8 -> (B,3,LH,LW) float32."""
+        B = frames.shape[0]
+        self._chk(frames, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "frames")
+        if out is None:
+            out = torch.empty((B, 3, self.LH, self.LW), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_preprocess(self._h, frames.data_ptr(), B, out.data_ptr(), self._stream()),
+                  "vti_preprocess")
+        return out
+
+    def _check_head(self, p3, p4, p5, coef, proto):
+        B = p3.shape[0]
+        for t, (hh, ww), nm in zip((p3, p4, p5), self.level_shapes, ("p3", "p4", "p5")):
+            self._chk(t, torch.float32, (B, 64 + self.cfg.nc, hh, ww), nm)
+        self._chk(coef, torch.float32, (B, 32, self.A), "coef")
+        self._chk(proto, torch.float32, (B, 32, self.ph, self.pw), "proto")
+        return B
+
+    def postprocess(self, p3, p4, p5, coef, proto, outputs=None, export_masks: bool = False):
+        """K2+K3+K4.  Returns (dets, counts, masks) device tensors (see alloc_outputs)."""
+        B = self._check_head(p3, p4, p5, coef, proto)
+        dets, counts, results, masks = outputs if outputs is not None else self.alloc_outputs(B, export_masks)
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_postprocess(self._h, p3.data_ptr(), p4.data_ptr(), p5.data_ptr(), coef.data_ptr(),
+                                           proto.data_ptr(), B, dets.data_ptr(), counts.data_ptr(),
+                                           masks.data_ptr() if masks is not None else None, self._stream()),
+                  "vti_postprocess")
+        return dets, counts, masks
+
+    def measure(self, dets, counts, results=None):
+        """K5.  Completes the records in place; returns the per-frame result tensor."""
+        B = dets.shape[0]
+        if results is None:
+            results = torch.empty((B, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_measure(self._h, B, dets.data_ptr(), counts.data_ptr(), results.data_ptr(),
+                                       self._stream()), "vti_measure")
+        return results
+
+    def post_measure(self, p3, p4, p5, coef, proto, outputs=None, export_masks: bool = False):
+        B = self._check_head(p3, p4, p5, coef, proto)
+        dets, counts, results, masks = outputs if outputs is not None else self.alloc_outputs(B, export_masks)
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_post_measure(self._h, p3.data_ptr(), p4.data_ptr(), p5.data_ptr(), coef.data_ptr(),
+                                            proto.data_ptr(), B, dets.data_ptr(), counts.data_ptr(),
+                                            masks.data_ptr() if masks is not None else None, results.data_ptr(),
+                                            self._stream()), "vti_post_measure")
+        return dets, counts, results, masks
+
+    def process_host(self, frames: np.ndarray, p3, p4, p5, coef, proto, want_net_in: bool = False, out=None):
+        """End-to-end with HOST numpy buffers (ideally pinned): H2D, K1..K5, D2H.  Returns (dets, counts, results[, net_in])."""
+        B = frames.shape[0]
+        if out is None:
+            out = (np.empty((B, self.cfg.max_det), DET_DTYPE), np.empty((B,), np.int32), np.empty((B,), RESULT_DTYPE))
+        dets, counts, results = out
+        net_in = np.empty((B, 3, self.LH, self.LW), np.float32) if want_net_in else None
+        arrs = [frames, p3, p4, p5, coef, proto]
+        for a_ in arrs:
+            if not a_.flags["C_CONTIGUOUS"]:
+                raise ValueError("process_host needs C-contiguous host arrays")
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_process_host(self._h, *[a_.ctypes.data for a_ in arrs], B,
+                                            net_in.ctypes.data if net_in is not None else None, dets.ctypes.data,
+                                            counts.ctypes.data, results.ctypes.data), "vti_process_host")
+        return (dets, counts, results, net_in) if want_net_in else (dets, counts, results)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vti_launch_count(self._h))
+
+    # ------------------------------------------------------------------------------------------------ readback
+    @staticmethod
+    def dets_to_numpy(dets: torch.Tensor) -> np.ndarray:
+        return dets.cpu().numpy().view(DET_DTYPE).reshape(dets.shape[0], dets.shape[1])
+
+    @staticmethod
+    def results_to_numpy(results: torch.Tensor) -> np.ndarray:
+        return results.cpu().numpy().view(RESULT_DTYPE).reshape(results.shape[0])
+
+    def unpack_masks(self, masks: torch.Tensor, b: int, n: int) -> torch.Tensor:
+        """Bit-packed (max_det, LH, LW/32) int32 -> (n, LH, LW) float32 0/1, like Results.masks.data."""
+        w = masks[b, :n].to(torch.int64) & 0xFFFFFFFF
+        bits = (w.unsqueeze(-1) >> torch.arange(32, device=masks.device)) & 1
+        return bits.reshape(n, self.LH, self.LW).to(torch.float32)
