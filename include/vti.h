@@ -168,6 +168,12 @@ int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, cons
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t vti_launch_count(const vti_handle* h);
 
+/* Per-kernel timing with CUDA events recorded on the caller's stream around each kernel (off by default).
+ * vti_get_stage_ms synchronises on the events of the most recent vti_preprocess / vti_postprocess / vti_measure
+ * calls and returns their durations in ms: ms[0..4] = K1, K2, K3, K4, K5 (-1 where no event pair was recorded). */
+int vti_set_profiling(vti_handle* h, int on);
+int vti_get_stage_ms(vti_handle* h, float ms[5]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ EXPORTS = [
     "vti_last_error", "vti_abi_version", "vti_plan_geometry", "vti_plan_resize_taps_x", "vti_plan_resize_taps_y",
     "vti_plan_undistort_map", "vti_plan_nearest_map", "vti_create", "vti_destroy", "vti_get_geometry",
     "vti_preprocess", "vti_postprocess", "vti_measure", "vti_post_measure", "vti_process_host", "vti_launch_count",
+    "vti_set_profiling", "vti_get_stage_ms",
 ]
 
 _lib = None
@@ -88,6 +89,8 @@ def load():
     lib.vti_process_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.vti_launch_count.argtypes = [vp]
     lib.vti_launch_count.restype = i64
+    lib.vti_set_profiling.argtypes = [vp, i32]
+    lib.vti_get_stage_ms.argtypes = [vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

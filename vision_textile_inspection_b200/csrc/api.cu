@@ -160,6 +160,8 @@ extern "C" void vti_destroy(vti_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < 8; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
 }
 
@@ -264,6 +266,33 @@ extern "C" int vti_get_geometry(const vti_handle* h, vti_geometry* out) {
 
 extern "C" int64_t vti_launch_count(const vti_handle* h) { return h ? h->launches : 0; }
 
+static inline void mark(vti_handle* h, int i, cudaStream_t s) {
+    if (!h->profiling) return;
+    if (cudaEventRecord(h->ev[i], s) == cudaSuccess) h->ev_set[i] = true;
+}
+
+extern "C" int vti_set_profiling(vti_handle* h, int on) {
+    if (!h) return VTI_EINVAL;
+    if (on && !h->ev[0])
+        for (int i = 0; i < 8; ++i) VTI_CUDA(cudaEventCreate(&h->ev[i]));
+    h->profiling = on ? 1 : 0;
+    for (int i = 0; i < 8; ++i) h->ev_set[i] = false;
+    return VTI_OK;
+}
+
+extern "C" int vti_get_stage_ms(vti_handle* h, float ms[5]) {
+    if (!h || !ms) return VTI_EINVAL;
+    const int a[5] = {0, 2, 3, 4, 6}, b[5] = {1, 3, 4, 5, 7};
+    for (int k = 0; k < 5; ++k) {
+        ms[k] = -1.0f;
+        if (h->ev[0] && h->ev_set[a[k]] && h->ev_set[b[k]]) {
+            VTI_CUDA(cudaEventSynchronize(h->ev[b[k]]));
+            VTI_CUDA(cudaEventElapsedTime(&ms[k], h->ev[a[k]], h->ev[b[k]]));
+        }
+    }
+    return VTI_OK;
+}
+
 static int check_batch(const vti_handle* h, int B) {
     if (!h || B < 1 || B > h->p.max_batch) {
         vti_set_error("batch size out of range for this handle (max_batch)");
@@ -276,7 +305,10 @@ extern "C" int vti_preprocess(vti_handle* h, const uint8_t* frames, int B, float
     int rc = check_batch(h, B);
     if (rc) return rc;
     if (!frames || !net_in) { vti_set_error("vti_preprocess: null buffer"); return VTI_EINVAL; }
-    return vti_launch_k1(h, frames, B, net_in, (cudaStream_t)stream);
+    mark(h, 0, (cudaStream_t)stream);
+    rc = vti_launch_k1(h, frames, B, net_in, (cudaStream_t)stream);
+    mark(h, 1, (cudaStream_t)stream);
+    return rc;
 }
 
 extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, const float* p5, const float* coef,
@@ -289,9 +321,14 @@ extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, 
         return VTI_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    mark(h, 2, s);
     if ((rc = vti_launch_k2(h, p3, p4, p5, B, s))) return rc;
+    mark(h, 3, s);
     if ((rc = vti_launch_k3(h, coef, B, dets, counts, s))) return rc;
-    return vti_launch_k4(h, proto, B, dets, counts, masks, s);
+    mark(h, 4, s);
+    rc = vti_launch_k4(h, proto, B, dets, counts, masks, s);
+    mark(h, 5, s);
+    return rc;
 }
 
 extern "C" int vti_measure(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* results,
@@ -299,7 +336,10 @@ extern "C" int vti_measure(vti_handle* h, int B, vti_det* dets, const int32_t* c
     int rc = check_batch(h, B);
     if (rc) return rc;
     if (!dets || !counts || !results) { vti_set_error("vti_measure: null buffer"); return VTI_EINVAL; }
-    return vti_launch_k5(h, B, dets, counts, results, (cudaStream_t)stream);
+    mark(h, 6, (cudaStream_t)stream);
+    rc = vti_launch_k5(h, B, dets, counts, results, (cudaStream_t)stream);
+    mark(h, 7, (cudaStream_t)stream);
+    return rc;
 }
 
 extern "C" int vti_post_measure(vti_handle* h, const float* p3, const float* p4, const float* p5, const float* coef,

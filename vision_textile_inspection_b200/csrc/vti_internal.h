@@ -49,6 +49,10 @@ struct vti_handle {
     uint8_t* d_frames; float* d_net_in; float* d_p[3]; float* d_coef; float* d_proto;
     vti_det* d_dets; int32_t* d_counts; vti_frame_result* d_results;
     size_t staged_batch;
+    // ---- optional per-kernel event timing
+    int profiling;
+    cudaEvent_t ev[8];       // K1: 0,1   K2: 2,3   K3: 3,4   K4: 4,5   K5: 6,7
+    bool ev_set[8];
 };
 
 void vti_set_error(const std::string& s);

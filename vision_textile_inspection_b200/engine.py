@@ -219,6 +219,15 @@ class InspectionEngine:
     def launch_count(self) -> int:
         return int(self.lib.vti_launch_count(self._h))
 
+    def set_profiling(self, on: bool):
+        check(self.lib.vti_set_profiling(self._h, int(on)), "vti_set_profiling")
+
+    def stage_ms(self) -> list:
+        """[K1, K2, K3, K4, K5] durations (ms) of the most recent calls, CUDA events on the launching stream."""
+        ms = (C.c_float * 5)()
+        check(self.lib.vti_get_stage_ms(self._h, ms), "vti_get_stage_ms")
+        return [float(v) for v in ms]
+
     # ------------------------------------------------------------------------------------------------ readback
     @staticmethod
     def dets_to_numpy(dets: torch.Tensor) -> np.ndarray:
