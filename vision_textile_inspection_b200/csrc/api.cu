@@ -156,7 +156,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutY.first, h->lutY.last, h->lutX.cnt, h->lutX.sum, h->lutX.first, h->lutX.last, h->d_xmap,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
-                    h->d_counts, h->d_results};
+                    h->d_counts, h->d_results, h->d_k1_tiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -216,21 +216,29 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     }
     if ((rc = upload(&h->d_tap_x_idx, xi)) || (rc = upload(&h->d_tap_x_a, xa)) || (rc = upload(&h->d_tap_y_i, yi)) ||
         (rc = upload(&h->d_tap_y_b, yb))) { vti_destroy(h); return rc; }
-    if (p->undistort) {
-        std::vector<int32_t> ix((size_t)fh * fw), iy((size_t)fh * fw), packed((size_t)fh * fw);
-        vti_plan_undistort_map(p->K, p->dist, fh, fw, ix.data(), iy.data());
-        for (int v = 0; v < fh; ++v)
-            for (int u = 0; u < fw; ++u) {
-                const size_t i = (size_t)v * fw + u;
-                const int dx = ix[i] - 32 * u, dy = iy[i] - 32 * v;
-                if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) {
-                    vti_set_error("vti_create: lens displacement exceeds +-1024 px, unsupported");
-                    vti_destroy(h);
-                    return VTI_EINVAL;
+    {
+        std::vector<int32_t> ix, iy;
+        if (p->undistort) {
+            ix.resize((size_t)fh * fw); iy.resize((size_t)fh * fw);
+            std::vector<int32_t> packed((size_t)fh * fw);
+            vti_plan_undistort_map(p->K, p->dist, fh, fw, ix.data(), iy.data());
+            for (int v = 0; v < fh; ++v)
+                for (int u = 0; u < fw; ++u) {
+                    const size_t i = (size_t)v * fw + u;
+                    const int dx = ix[i] - 32 * u, dy = iy[i] - 32 * v;
+                    if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) {
+                        vti_set_error("vti_create: lens displacement exceeds +-1024 px, unsupported");
+                        vti_destroy(h);
+                        return VTI_EINVAL;
+                    }
+                    packed[i] = (int32_t)(((uint32_t)(uint16_t)(int16_t)dy << 16) | (uint32_t)(uint16_t)(int16_t)dx);
                 }
-                packed[i] = (int32_t)(((uint32_t)(uint16_t)(int16_t)dy << 16) | (uint32_t)(uint16_t)(int16_t)dx);
-            }
-        if ((rc = upload(&h->d_und_lut, packed))) { vti_destroy(h); return rc; }
+            if ((rc = upload(&h->d_und_lut, packed))) { vti_destroy(h); return rc; }
+        }
+        if ((rc = vti_k1_plan(h, xi, yi, p->undistort ? &ix : nullptr, p->undistort ? &iy : nullptr))) {
+            vti_destroy(h);
+            return rc;
+        }
     }
     // ---- measurement tables
     if ((rc = build_axis_lut(fh, g.LH, &h->lutY, nullptr)) || (rc = build_axis_lut(fw, g.LW, &h->lutX, &h->d_xmap))) {

@@ -4,23 +4,33 @@
 // BasePredictor.preprocess, reached from /root/reference/measurement.py:205-210.
 // Spec: oracle/cv_fixed.py (bit-exact integer formulas, pinned against cv2 in tests/test_oracle_cv.py).
 //
-// One CTA produces a TY x TX tile of the letterboxed output for all three planes.
-//   phase A  stage the source footprint of the tile in shared memory as planar uint8; with undistort on, every
-//            staged pixel is the 4-tap fixed-point remap of the raw frame (the intermediate uint8 rounding of
-//            cv2.undistort is preserved -- a single composed bilinear sample would NOT be bit-exact)
-//   phase B  11-bit H pass + V pass of cv2.resize from shared memory, /255 through a 256-entry table
-//            (true division, not *1/255), 128-bit coalesced stores of the fp32 planes; pad = 114/255.
-// HBM traffic: frame read once (tile halos hit L2) + 12*LH*LW written once.
+// One CTA produces a TY x TX tile of the letterboxed output for all three planes.  Pixels travel through shared
+// memory as ONE 32-bit word each (B | G<<8 | R<<16), so a bilinear tap is a single LDS for all three channels.
+//   stage   MODE_RAW   the raw-frame bounding box of the tile's remap taps (host-planned per tile) is copied with
+//                      aligned 32-bit loads, 12 bytes -> 4 packed pixels -> one 128-bit shared store
+//           MODE_PLAIN the tile's source footprint itself is staged that way (no undistort)
+//           MODE_GATHER generic fallback: per-pixel byte gathers from global (>= 2x shrink, odd widths, huge warps)
+//   remap   (undistort only) every footprint pixel = 4-tap fixed-point remap of the staged raw pixels with OpenCV's
+//           5-bit fractions; B and R ride in one register (two 16-bit lanes), the two rows' G in another.  The
+//           intermediate uint8 rounding of cv2.undistort is preserved -- a composed single bilinear sample is NOT
+//           bit-exact.
+//   resize  11-bit H pass + V pass of cv2.resize from shared memory, /255 through a 256-entry table (a true
+//           division, not *1/255), warp-coalesced stores of the three fp32 planes; pad = 114/255.
+// HBM traffic: frame read once (tile halos hit L2) + 12*LH*LW written once; the 4 B/px remap table is L2-resident
+// across the batch.
+#include <algorithm>
+#include <vector>
+
 #include "vti_internal.h"
 
 namespace {
 
-constexpr int TX = 128;
-constexpr int TY = 16;
+constexpr int TX = VTI_K1_TX;
+constexpr int TY = VTI_K1_TY;
 constexpr int K1_THREADS = 256;
 constexpr int MAXROWS = 2 * TY + 2;
 constexpr int MAXCOLS = 2 * TX + 2;
-constexpr int PITCH = 272;   // >= MAXCOLS, multiple of 16
+enum { MODE_PLAIN = 0, MODE_RAW = 1, MODE_GATHER = 2 };
 
 struct K1Args {
     const uint8_t* frames;
@@ -30,49 +40,84 @@ struct K1Args {
     const int32_t* tap_y_i;     // [new_h][2]
     const int16_t* tap_y_b;     // [new_h][2]
     const int32_t* und_lut;     // [h*w] (dy16 << 16) | (dx16 & 0xffff)
+    const int4* tile_box;       // MODE_RAW: per tile (bx0, by0, bw, bh | interior << 30)
     int h, w, new_h, new_w, top, left, LH, LW;
-    int mode;                   // 1 bilinear (also used for the identity copy), 2 exact-2x area
+    int area2x;                 // exact-2x shrink: OpenCV's INTER_AREA switch
     int flip;
+    int pitch_u;                // words per row of the footprint buffer
+    int rows_u;                 // rows of the footprint buffer
+    int undistort;
 };
 
-__device__ __forceinline__ int remap_px(const uint8_t* __restrict__ f, int h, int w, int sy, int sx, int lut, int ch) {
-    const int dx = (int)(short)(lut & 0xffff);
-    const int dy = lut >> 16;
-    const int ix = sx * 32 + dx, iy = sy * 32 + dy;
-    const int x = ix >> 5, y = iy >> 5, fx = ix & 31, fy = iy & 31;
-    const bool x0 = (unsigned)x < (unsigned)w, x1 = (unsigned)(x + 1) < (unsigned)w;
-    const bool y0 = (unsigned)y < (unsigned)h, y1 = (unsigned)(y + 1) < (unsigned)h;
-    const uint8_t* r0 = f + ((size_t)y * w + x) * 3 + ch;
-    const uint8_t* r1 = r0 + (size_t)w * 3;
-    const int p00 = (y0 && x0) ? r0[0] : 0;
-    const int p01 = (y0 && x1) ? r0[3] : 0;
-    const int p10 = (y1 && x0) ? r1[0] : 0;
-    const int p11 = (y1 && x1) ? r1[3] : 0;
-    const int acc = p00 * ((32 - fx) * (32 - fy)) + p01 * (fx * (32 - fy)) + p10 * ((32 - fx) * fy) + p11 * (fx * fy);
-    return (acc + 512) >> 10;   // == (sum(w15 * p) + 2^14) >> 15 because every 15-bit weight is 32 * (10-bit weight)
+__device__ __forceinline__ unsigned pack_px(unsigned b0, unsigned b1, unsigned b2, int flip) {
+    return flip ? (b2 | (b1 << 8) | (b0 << 16)) : (b0 | (b1 << 8) | (b2 << 16));
 }
 
-template <bool UNDISTORT>
+// Copy `npx` pixels (multiple of 4) starting at pixel x0 (multiple of 4) of one frame row into packed words.
+// row must be 4-byte aligned (w % 4 == 0).  dst[i] receives pixel x0 + i for i in [keep_lo, keep_hi).
+__device__ __forceinline__ void stage_row_packed(const uint8_t* __restrict__ row, int x0, int npx, unsigned* dst,
+                                                 int keep_lo, int keep_hi, int lane, int flip) {
+    const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(row + (size_t)x0 * 3);
+    for (int g = lane; g < (npx >> 2); g += 32) {
+        const unsigned w0 = __ldg(src + 3 * g), w1 = __ldg(src + 3 * g + 1), w2 = __ldg(src + 3 * g + 2);
+        unsigned p0 = w0 & 0xFFFFFFu;
+        unsigned p1 = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
+        unsigned p2 = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
+        unsigned p3 = w2 >> 8;
+        if (flip) {
+            p0 = __byte_perm(p0, 0, 0x3012); p1 = __byte_perm(p1, 0, 0x3012);
+            p2 = __byte_perm(p2, 0, 0x3012); p3 = __byte_perm(p3, 0, 0x3012);
+        }
+        const int i = 4 * g;
+        if (i >= keep_lo && i + 3 < keep_hi) {
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(p0, p1, p2, p3);
+        } else {
+            if (i >= keep_lo && i < keep_hi) dst[i] = p0;
+            if (i + 1 >= keep_lo && i + 1 < keep_hi) dst[i + 1] = p1;
+            if (i + 2 >= keep_lo && i + 2 < keep_hi) dst[i + 2] = p2;
+            if (i + 3 >= keep_lo && i + 3 < keep_hi) dst[i + 3] = p3;
+        }
+    }
+}
+
+// 4-tap fixed-point remap of packed pixels: returns the packed uint8 result of cv2.remap(INTER_LINEAR).
+//   acc_c = (32-fy) * [(32-fx) p00 + fx p01] + fy * [(32-fx) p10 + fx p11];  out = (acc + 512) >> 10
+// (== (sum(w15 * p) + 2^14) >> 15: every 15-bit OpenCV weight is exactly 32 * the 10-bit product weight)
+__device__ __forceinline__ unsigned remap_packed(unsigned t00, unsigned t01, unsigned t10, unsigned t11, int fx, int fy) {
+    const unsigned wx0 = 32 - fx, wy0 = 32 - fy;
+    const unsigned br0 = (t00 & 0x00FF00FFu) * wx0 + (t01 & 0x00FF00FFu) * fx;       // B | R<<16, each <= 8160
+    const unsigned br1 = (t10 & 0x00FF00FFu) * wx0 + (t11 & 0x00FF00FFu) * fx;
+    const unsigned g01 = __byte_perm(t00, t10, 0x3531) * wx0 + __byte_perm(t01, t11, 0x3531) * fx;  // G0 | G1<<16
+    const unsigned b = ((br0 & 0xFFFFu) * wy0 + (br1 & 0xFFFFu) * fy + 512u) >> 10;
+    const unsigned r = ((br0 >> 16) * wy0 + (br1 >> 16) * fy + 512u) >> 10;
+    const unsigned g = ((g01 & 0xFFFFu) * wy0 + (g01 >> 16) * fy + 512u) >> 10;
+    return b | (g << 8) | (r << 16);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a) {
-    __shared__ __align__(16) uint8_t s_px[3][MAXROWS][PITCH];
+    extern __shared__ __align__(16) unsigned s_dyn[];      // [footprint rows][pitch_u] then the raw box (MODE_RAW)
     __shared__ float s_div[256];
     __shared__ int s_rowsrc[MAXROWS];
-    __shared__ int s_colsrc[MAXCOLS];
+    __shared__ int s_colsrc[MAXCOLS + 4];
+    __shared__ int4 s_rowtap[TY];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
     const int b = blockIdx.z;
     const uint8_t* __restrict__ frame = a.frames + (size_t)b * a.h * a.w * 3;
     float* __restrict__ out = a.out + (size_t)b * 3 * a.LH * a.LW;
+    unsigned* s_und = s_dyn;
 
     s_div[tid] = __fdiv_rn((float)tid, 255.0f);
 
-    // resized-image rows / cols covered by this tile
     const int ry_lo = max(Y0 - a.top, 0), ry_hi = min(Y0 + TY - 1 - a.top, a.new_h - 1);
     const int rx_lo = max(X0 - a.left, 0), rx_hi = min(X0 + TX - 1 - a.left, a.new_w - 1);
     const bool any = (ry_lo <= ry_hi) && (rx_lo <= rx_hi);
     int nrows = 0, ncols = 0, r_lo = 0, c_lo = 0;
     bool row_contig = true, col_contig = true;
+    // MODE_PLAIN stages whole 4-pixel groups with 128-bit shared stores: its column origin is 4-aligned
+    const bool vec_plain = (MODE == MODE_PLAIN) && ((a.w & 3) == 0);
     if (any) {
         r_lo = a.tap_y_i[2 * ry_lo];
         const int r_hi = a.tap_y_i[2 * ry_hi + 1];
@@ -81,95 +126,238 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
         c_lo = a.tap_x_idx[rx_lo];
         const int c_hi = min(a.tap_x_idx[rx_hi] + 1, a.w - 1);
         col_contig = (c_hi - c_lo + 1) <= MAXCOLS;
+        if (col_contig && vec_plain) c_lo &= ~3;
         ncols = col_contig ? (c_hi - c_lo + 1) : 2 * (rx_hi - rx_lo + 1);
         for (int i = tid; i < nrows; i += K1_THREADS)
             s_rowsrc[i] = row_contig ? (r_lo + i) : a.tap_y_i[2 * ry_lo + i];
         for (int i = tid; i < ncols; i += K1_THREADS)
             s_colsrc[i] = col_contig ? (c_lo + i) : min(a.tap_x_idx[rx_lo + (i >> 1)] + (i & 1), a.w - 1);
+        if (tid < TY) {
+            const int ry = Y0 + tid - a.top;
+            int4 t = make_int4(0, 0, 0, 0);
+            if (ry >= 0 && ry < a.new_h) {
+                t.x = row_contig ? (a.tap_y_i[2 * ry] - r_lo) : 2 * (ry - ry_lo);
+                t.y = row_contig ? (a.tap_y_i[2 * ry + 1] - r_lo) : 2 * (ry - ry_lo) + 1;
+                t.z = a.tap_y_b[2 * ry];
+                t.w = a.tap_y_b[2 * ry + 1];
+            }
+            s_rowtap[tid] = t;
+        }
     }
     __syncthreads();
 
-    // ---- phase A: stage source pixels
+    // ------------------------------------------------------------------------------------------------ stage
     if (any) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < nrows; r += K1_THREADS / 32) {
-            const int sy = s_rowsrc[r];
-            for (int c = lane; c < ncols; c += 32) {
-                const int sx = s_colsrc[c];
-                if (UNDISTORT) {
+        if (MODE == MODE_PLAIN) {
+            if (col_contig && vec_plain) {
+                const int npx = (ncols + 3) & ~3;          // c_lo is 4-aligned, w % 4 == 0: stays inside the row
+                for (int r = warp; r < nrows; r += K1_THREADS / 32)
+                    stage_row_packed(frame + (size_t)s_rowsrc[r] * a.w * 3, c_lo, npx, s_und + r * a.pitch_u, 0, npx,
+                                     lane, a.flip);
+            } else {
+                for (int r = warp; r < nrows; r += K1_THREADS / 32) {
+                    const uint8_t* __restrict__ row = frame + (size_t)s_rowsrc[r] * a.w * 3;
+                    for (int c = lane; c < ncols; c += 32) {
+                        const uint8_t* p = row + (size_t)s_colsrc[c] * 3;
+                        s_und[r * a.pitch_u + c] = pack_px(__ldg(p), __ldg(p + 1), __ldg(p + 2), a.flip);
+                    }
+                }
+            }
+        } else if (MODE == MODE_RAW) {
+            unsigned* s_raw = s_dyn + a.rows_u * a.pitch_u;
+            const int4 box = a.tile_box[blockIdx.y * gridDim.x + blockIdx.x];
+            const int bx0 = box.x, by0 = box.y, bw = box.z, bh = box.w & 0xFFFF;
+            const bool interior = (box.w >> 30) & 1;
+            for (int r = warp; r < bh; r += K1_THREADS / 32)
+                stage_row_packed(frame + (size_t)(by0 + r) * a.w * 3, bx0, bw, s_raw + r * bw, 0, bw, lane, a.flip);
+            __syncthreads();
+            for (int r = warp; r < nrows; r += K1_THREADS / 32) {
+                const int sy = s_rowsrc[r];
+                const int32_t* __restrict__ lrow = a.und_lut + (size_t)sy * a.w;
+                for (int c = lane; c < ncols; c += 32) {
+                    const int sx = c_lo + c;
+                    const int lut = __ldg(lrow + sx);
+                    const int ix = sx * 32 + (int)(short)(lut & 0xffff), iy = sy * 32 + (lut >> 16);
+                    const int x = ix >> 5, y = iy >> 5;
+                    const int idx = (y - by0) * bw + (x - bx0);
+                    unsigned t00, t01, t10, t11;
+                    if (interior) {
+                        t00 = s_raw[idx]; t01 = s_raw[idx + 1]; t10 = s_raw[idx + bw]; t11 = s_raw[idx + bw + 1];
+                    } else {
+                        const bool x0 = (unsigned)x < (unsigned)a.w, x1 = (unsigned)(x + 1) < (unsigned)a.w;
+                        const bool y0 = (unsigned)y < (unsigned)a.h, y1 = (unsigned)(y + 1) < (unsigned)a.h;
+                        t00 = (y0 && x0) ? s_raw[idx] : 0u;
+                        t01 = (y0 && x1) ? s_raw[idx + 1] : 0u;
+                        t10 = (y1 && x0) ? s_raw[idx + bw] : 0u;
+                        t11 = (y1 && x1) ? s_raw[idx + bw + 1] : 0u;
+                    }
+                    s_und[r * a.pitch_u + c] = remap_packed(t00, t01, t10, t11, ix & 31, iy & 31);
+                }
+            }
+        } else {   // MODE_GATHER
+            for (int r = warp; r < nrows; r += K1_THREADS / 32) {
+                const int sy = s_rowsrc[r];
+                for (int c = lane; c < ncols; c += 32) {
+                    const int sx = s_colsrc[c];
                     const int lut = __ldg(a.und_lut + (size_t)sy * a.w + sx);
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        s_px[ch][r][c] = (uint8_t)remap_px(frame, a.h, a.w, sy, sx, lut, a.flip ? 2 - ch : ch);
-                } else {
-                    const uint8_t* p = frame + ((size_t)sy * a.w + sx) * 3;
-                    const uint8_t v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-                    s_px[0][r][c] = a.flip ? v2 : v0;
-                    s_px[1][r][c] = v1;
-                    s_px[2][r][c] = a.flip ? v0 : v2;
+                    const int ix = sx * 32 + (int)(short)(lut & 0xffff), iy = sy * 32 + (lut >> 16);
+                    const int x = ix >> 5, y = iy >> 5;
+                    const bool x0 = (unsigned)x < (unsigned)a.w, x1 = (unsigned)(x + 1) < (unsigned)a.w;
+                    const bool y0 = (unsigned)y < (unsigned)a.h, y1 = (unsigned)(y + 1) < (unsigned)a.h;
+                    const uint8_t* q0 = frame + ((size_t)y * a.w + x) * 3;
+                    const uint8_t* q1 = q0 + (size_t)a.w * 3;
+                    const unsigned t00 = (y0 && x0) ? pack_px(q0[0], q0[1], q0[2], a.flip) : 0u;
+                    const unsigned t01 = (y0 && x1) ? pack_px(q0[3], q0[4], q0[5], a.flip) : 0u;
+                    const unsigned t10 = (y1 && x0) ? pack_px(q1[0], q1[1], q1[2], a.flip) : 0u;
+                    const unsigned t11 = (y1 && x1) ? pack_px(q1[3], q1[4], q1[5], a.flip) : 0u;
+                    s_und[r * a.pitch_u + c] = remap_packed(t00, t01, t10, t11, ix & 31, iy & 31);
                 }
             }
         }
     }
     __syncthreads();
 
-    // ---- phase B: resize + normalise + store.  item = (plane, tile row, group of 4 columns)
+    // ----------------------------------------------------------------------------------------------- resize
+    // warp = (column group of 32, row group of 8); lane = output column => conflict-free LDS, coalesced STG
     const float pad = s_div[114];
-    for (int item = tid; item < 3 * TY * (TX / 4); item += K1_THREADS) {
-        const int xq = item % (TX / 4);
-        const int j = (item / (TX / 4)) % TY;
-        const int ch = item / (TY * (TX / 4));
-        const int Y = Y0 + j, X = X0 + xq * 4;
-        if (Y >= a.LH || X >= a.LW) continue;
+    const int X = X0 + 32 * (warp & 3) + lane;
+    if (X >= a.LW) return;
+    const int rx = X - a.left;
+    const bool xin = (rx >= 0) && (rx < a.new_w);
+    int cs0 = 0, cs1 = 0, a0 = 0, a1 = 0;
+    if (xin && any) {
+        if (col_contig) {
+            const int sx = a.tap_x_idx[rx];
+            cs0 = sx - c_lo;
+            cs1 = min(sx + 1, a.w - 1) - c_lo;
+        } else {
+            cs0 = 2 * (rx - rx_lo);
+            cs1 = cs0 + 1;
+        }
+        a0 = a.tap_x_a[2 * rx];
+        a1 = a.tap_x_a[2 * rx + 1];
+    }
+    const size_t plane = (size_t)a.LH * a.LW;
+#pragma unroll 2
+    for (int i = 0; i < TY / 2; ++i) {
+        const int j = (warp >> 2) * (TY / 2) + i;
+        const int Y = Y0 + j;
+        if (Y >= a.LH) break;
         const int ry = Y - a.top;
-        float4 o = make_float4(pad, pad, pad, pad);
-        if (ry >= 0 && ry < a.new_h) {
-            int rs0, rs1;
-            if (row_contig) {
-                rs0 = a.tap_y_i[2 * ry] - r_lo;
-                rs1 = a.tap_y_i[2 * ry + 1] - r_lo;
-            } else {
-                rs0 = 2 * (ry - ry_lo);
-                rs1 = rs0 + 1;
-            }
-            const int b0 = a.tap_y_b[2 * ry], b1 = a.tap_y_b[2 * ry + 1];
-            const uint8_t* row0 = s_px[ch][rs0];
-            const uint8_t* row1 = s_px[ch][rs1];
-            float v[4];
+        float v0 = pad, v1 = pad, v2 = pad;
+        if (xin && ry >= 0 && ry < a.new_h) {
+            const int4 rt = s_rowtap[j];
+            const unsigned* row0 = s_und + rt.x * a.pitch_u;
+            const unsigned* row1 = s_und + rt.y * a.pitch_u;
+            const unsigned t00 = row0[cs0], t01 = row0[cs1], t10 = row1[cs0], t11 = row1[cs1];
+            int q[3];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int rx = X + k - a.left;
-                v[k] = pad;
-                if (rx >= 0 && rx < a.new_w) {
-                    int cs0, cs1;
-                    if (col_contig) {
-                        const int sx = a.tap_x_idx[rx];
-                        cs0 = sx - c_lo;
-                        cs1 = min(sx + 1, a.w - 1) - c_lo;
-                    } else {
-                        cs0 = 2 * (rx - rx_lo);
-                        cs1 = cs0 + 1;
-                    }
-                    const int p00 = row0[cs0], p01 = row0[cs1], p10 = row1[cs0], p11 = row1[cs1];
-                    int q;
-                    if (a.mode == 2) {
-                        q = (p00 + p01 + p10 + p11 + 2) >> 2;
-                    } else {
-                        const int a0 = a.tap_x_a[2 * rx], a1 = a.tap_x_a[2 * rx + 1];
-                        const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
-                        q = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-                        q = min(max(q, 0), 255);
-                    }
-                    v[k] = s_div[q];
+            for (int ch = 0; ch < 3; ++ch) {
+                const int p00 = (t00 >> (8 * ch)) & 255, p01 = (t01 >> (8 * ch)) & 255;
+                const int p10 = (t10 >> (8 * ch)) & 255, p11 = (t11 >> (8 * ch)) & 255;
+                if (a.area2x) {
+                    q[ch] = (p00 + p01 + p10 + p11 + 2) >> 2;
+                } else {
+                    const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
+                    const int o = (((rt.z * (S0 >> 4)) >> 16) + ((rt.w * (S1 >> 4)) >> 16) + 2) >> 2;
+                    q[ch] = min(max(o, 0), 255);
                 }
             }
-            o = make_float4(v[0], v[1], v[2], v[3]);
+            v0 = s_div[q[0]]; v1 = s_div[q[1]]; v2 = s_div[q[2]];
         }
-        *reinterpret_cast<float4*>(out + ((size_t)ch * a.LH + Y) * a.LW + X) = o;
+        float* o = out + (size_t)Y * a.LW + X;
+        o[0] = v0;
+        o[plane] = v1;
+        o[2 * plane] = v2;
     }
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------- host plan
+// Mirrors the kernel's per-tile footprint logic to size the shared buffers and, with undistort on, to find the
+// raw-frame bounding box of every tile's remap taps.
+int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy) {
+    const vti_geometry& g = h->g;
+    const int fw = h->p.frame_w, fh = h->p.frame_h;
+    const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
+    int ncols_max = 4, nrows_max = 1;
+    bool all_contig = true;
+    std::vector<int4> boxes((size_t)ntx * nty, make_int4(0, 0, 0, 0));
+    size_t raw_max = 0;
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+            const int X0 = tx * TX, Y0 = ty * TY;
+            const int ry_lo = std::max(Y0 - g.top, 0), ry_hi = std::min(Y0 + TY - 1 - g.top, g.new_h - 1);
+            const int rx_lo = std::max(X0 - g.left, 0), rx_hi = std::min(X0 + TX - 1 - g.left, g.new_w - 1);
+            if (ry_lo > ry_hi || rx_lo > rx_hi) continue;
+            const int r_lo = yi[2 * ry_lo], r_hi = yi[2 * ry_hi + 1];
+            const bool rc = (r_hi - r_lo + 1) <= MAXROWS;
+            const int nrows = rc ? (r_hi - r_lo + 1) : 2 * (ry_hi - ry_lo + 1);
+            const int c_lo = xi[rx_lo], c_hi = std::min(xi[rx_hi] + 1, fw - 1);
+            const bool cc = (c_hi - c_lo + 1) <= MAXCOLS;
+            const int ncols = (cc ? (c_hi - c_lo + 1) : 2 * (rx_hi - rx_lo + 1)) + 6;   // + 4-alignment slack
+            nrows_max = std::max(nrows_max, nrows);
+            ncols_max = std::max(ncols_max, ncols);
+            all_contig = all_contig && rc && cc;
+            if (und_ix && rc && cc) {
+                int minx = INT32_MAX, miny = INT32_MAX, maxx = -1, maxy = -1;
+                bool interior = true;
+                for (int sy = r_lo; sy <= r_hi; ++sy)
+                    for (int sx = c_lo; sx <= c_hi; ++sx) {
+                        const size_t i = (size_t)sy * fw + sx;
+                        const int x = (*und_ix)[i] >> 5, y = (*und_iy)[i] >> 5;
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int xx = x + dx, yy = y + dy;
+                                if (xx < 0 || xx >= fw || yy < 0 || yy >= fh) { interior = false; continue; }
+                                minx = std::min(minx, xx); maxx = std::max(maxx, xx);
+                                miny = std::min(miny, yy); maxy = std::max(maxy, yy);
+                            }
+                    }
+                int4 bx = make_int4(0, 0, 4, 0);
+                if (maxx >= 0) {
+                    bx.x = minx & ~3;
+                    bx.z = std::min(((maxx + 1 + 3) & ~3), (fw + 3) & ~3) - bx.x;
+                    bx.y = miny;
+                    bx.w = maxy - miny + 1;
+                }
+                raw_max = std::max(raw_max, (size_t)bx.z * (bx.w & 0xFFFF));
+                if (bx.w > 0xFFFF) all_contig = false;
+                bx.w |= interior ? (1 << 30) : 0;
+                boxes[(size_t)ty * ntx + tx] = bx;
+            }
+        }
+    h->k1_pitch_u = (ncols_max + 3) & ~3;
+    h->k1_rows_u = nrows_max;
+    const size_t und_bytes = (size_t)nrows_max * h->k1_pitch_u * 4;
+    h->k1_mode = MODE_PLAIN;
+    h->k1_smem = und_bytes;
+    if (h->p.undistort) {
+        const size_t tot = und_bytes + raw_max * 4;
+        if (all_contig && (fw & 3) == 0 && tot <= 160 * 1024) {
+            h->k1_mode = MODE_RAW;
+            h->k1_smem = tot;
+            VTI_CUDA(cudaMalloc((void**)&h->d_k1_tiles, sizeof(int4) * boxes.size()));
+            VTI_CUDA(cudaMemcpy(h->d_k1_tiles, boxes.data(), sizeof(int4) * boxes.size(), cudaMemcpyHostToDevice));
+        } else {
+            h->k1_mode = MODE_GATHER;
+        }
+    }
+    {
+        if (h->k1_mode == MODE_RAW)
+            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)h->k1_smem));
+        else if (h->k1_mode == MODE_GATHER)
+            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_GATHER>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
+        else
+            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)h->k1_smem));
+    }
+    return VTI_OK;
+}
 
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s) {
     K1Args a;
@@ -180,17 +368,23 @@ int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cu
     a.tap_y_i = h->d_tap_y_i;
     a.tap_y_b = h->d_tap_y_b;
     a.und_lut = h->d_und_lut;
+    a.tile_box = h->d_k1_tiles;
     a.h = h->p.frame_h; a.w = h->p.frame_w;
     a.new_h = h->g.new_h; a.new_w = h->g.new_w;
     a.top = h->g.top; a.left = h->g.left;
     a.LH = h->g.LH; a.LW = h->g.LW;
-    a.mode = h->resize_mode;
+    a.area2x = (h->resize_mode == 2);
     a.flip = h->p.channel_flip;
+    a.pitch_u = h->k1_pitch_u;
+    a.rows_u = h->k1_rows_u;
+    a.undistort = h->p.undistort;
     dim3 grid((a.LW + TX - 1) / TX, (a.LH + TY - 1) / TY, B);
-    if (h->p.undistort)
-        k1_letterbox_kernel<true><<<grid, K1_THREADS, 0, s>>>(a);
+    if (h->k1_mode == MODE_RAW)
+        k1_letterbox_kernel<MODE_RAW><<<grid, K1_THREADS, h->k1_smem, s>>>(a);
+    else if (h->k1_mode == MODE_GATHER)
+        k1_letterbox_kernel<MODE_GATHER><<<grid, K1_THREADS, h->k1_smem, s>>>(a);
     else
-        k1_letterbox_kernel<false><<<grid, K1_THREADS, 0, s>>>(a);
+        k1_letterbox_kernel<MODE_PLAIN><<<grid, K1_THREADS, h->k1_smem, s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());
     return VTI_OK;

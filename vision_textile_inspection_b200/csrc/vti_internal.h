@@ -11,6 +11,8 @@
 static_assert(sizeof(vti_det) == 160, "vti_det must stay 160 bytes");
 
 #define VTI_CAND_CAP_MAX 16384
+#define VTI_K1_TX 128        // K1 output tile
+#define VTI_K1_TY 16
 
 // Per-axis letterbox-pixel -> frame-pixel multiplicity tables of cv2.resize(INTER_NEAREST) (measurement.py:78-79).
 // A letterbox row Y is hit by cnt[Y] frame rows whose indices sum to sum[Y]; first/last are the extreme frame rows.
@@ -32,7 +34,10 @@ struct vti_handle {
     int32_t* d_tap_x_idx;  int16_t* d_tap_x_a;    // [new_w], [new_w*2]
     int32_t* d_tap_y_i;    int16_t* d_tap_y_b;    // [new_h*2], [new_h*2]
     int32_t* d_und_lut;                            // [frame_h*frame_w] packed (dy16<<16 | dx16), undistort only
-    int resize_mode;                               // 0 copy, 1 bilinear, 2 exact-2x area
+    int resize_mode;                               // 1 bilinear (incl. identity taps), 2 exact-2x area
+    int k1_mode, k1_pitch_u, k1_rows_u;            // staging mode + shared footprint buffer shape (k1 plan)
+    size_t k1_smem;
+    int4* d_k1_tiles;                              // per-tile raw bounding boxes (undistort, MODE_RAW)
     // ---- measurement tables (device)
     AxisLut lutY, lutX;                            // [LH], [LW]
     int32_t* d_xmap;                               // [frame_w] frame col -> letterbox col
@@ -66,6 +71,8 @@ void vti_set_error(const std::string& s);
     } while (0)
 
 // kernel launchers (each returns VTI_OK / VTI_ECUDA)
+int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy);
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s);
 int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* p5, int B, cudaStream_t s);
 int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, cudaStream_t s);
