@@ -3,6 +3,7 @@
 //
 // Planning mirrors oracle/cv_fixed.py (bit-exact vs OpenCV) and ultralytics LetterBox geometry;
 // tests/test_abi_cpu.py checks these host functions against the oracle without a GPU.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -145,6 +146,15 @@ static int build_axis_lut(int frame_n, int lb_n, AxisLut* lut, int32_t** d_map) 
     if ((rc = upload(&lut->sum, sum))) return rc;
     if ((rc = upload(&lut->first, first))) return rc;
     if ((rc = upload(&lut->last, last))) return rc;
+    std::vector<int32_t> pc(lb_n + 1, 0), ps(lb_n + 1, 0), prev_last(lb_n, -1), next_first(lb_n, INT_MAX);
+    for (int i = 0; i < lb_n; ++i) {
+        pc[i + 1] = pc[i] + cnt[i];
+        ps[i + 1] = ps[i] + sum[i];
+        prev_last[i] = std::max(i ? prev_last[i - 1] : -1, last[i]);
+    }
+    for (int i = lb_n - 1; i >= 0; --i) next_first[i] = std::min(i + 1 < lb_n ? next_first[i + 1] : INT_MAX, first[i]);
+    if ((rc = upload(&lut->pc, pc)) || (rc = upload(&lut->ps, ps)) || (rc = upload(&lut->prev_last, prev_last)) ||
+        (rc = upload(&lut->next_first, next_first))) return rc;
     if (d_map) return upload(d_map, map);
     return VTI_OK;
 }
@@ -154,6 +164,8 @@ extern "C" void vti_destroy(vti_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_tap_x_idx, h->d_tap_x_a, h->d_tap_y_i, h->d_tap_y_b, h->d_und_lut, h->lutY.cnt, h->lutY.sum,
                     h->lutY.first, h->lutY.last, h->lutX.cnt, h->lutX.sum, h->lutX.first, h->lutX.last, h->d_xmap,
+                    h->lutY.pc, h->lutY.ps, h->lutY.prev_last, h->lutY.next_first, h->lutX.pc, h->lutX.ps,
+                    h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
                     h->d_counts, h->d_results, h->d_k1_tiles};

@@ -113,8 +113,12 @@ __device__ __forceinline__ bool env_median(const int32_t* envf, int w, int cx_in
 }
 
 __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) {
+    // everything thread 0 walks sequentially lives in shared memory (global round trips were 70 % of v1's time)
     __shared__ double s_cy[MAXN];
     __shared__ double s_tmp[MAXN];
+    __shared__ double s_w[MAXN];          // per stitch: width_mm (NaN = none)
+    __shared__ double s_d[MAXN];          // per final entry: dist_mm (NaN = none)
+    __shared__ unsigned s_flags[MAXN];    // per detection
     __shared__ short s_st[MAXN];          // stitch list -> det index
     __shared__ short s_sel[MAXN];         // selected -> stitch index
     __shared__ short s_fin[MAXN];
@@ -123,29 +127,28 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     __shared__ long long s_envsum;
     __shared__ int s_envcnt;
 
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int n = a.counts[b];
     vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
     int32_t* __restrict__ envf = a.env_frame + (size_t)b * a.w;
     const Camera& cam = a.cam;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    if (tid == 0) { s_envsum = 0; s_envcnt = 0; s_nfab = 0; }
+    if (tid == 0) { s_envsum = 0; s_envcnt = 0; s_nfab = 0; s_ns = 0; }
     // ---- finalize K4's statistics, frame-resolution envelope
     for (int k = tid; k < n; k += K5_THREADS) {
-        if (dets[k].m00 > 0) dets[k].flags |= VTI_F_HAS_MASK;
+        unsigned f = dets[k].flags;
+        if (dets[k].m00 > 0) { f |= VTI_F_HAS_MASK; dets[k].flags = f; }
         else { dets[k].col_min = -1; dets[k].col_max = -1; }
+        s_flags[k] = f;
     }
     const int* __restrict__ env = a.env + (size_t)b * a.LW;
-    for (int x = tid; x < a.w; x += K5_THREADS) {
-        int e = env[a.xmap[x]];
-        envf[x] = e;                       // variant 1 keeps INT_MAX = none until the rectangles are merged
-    }
+    for (int x = tid; x < a.w; x += K5_THREADS) envf[x] = env[a.xmap[x]];   // variant 1 keeps INT_MAX = none for now
     __syncthreads();
     if (a.variant == 1) {
         // mask-less fabric detection -> filled bbox rectangle (check_stitch_distance.py:331-334), upper envelope
         for (int k = 0; k < n; ++k) {
-            const unsigned f = dets[k].flags;
+            const unsigned f = s_flags[k];
             if (!(f & VTI_F_FABRIC) || (f & VTI_F_HAS_MASK)) continue;
             const int x1 = max(min(dets[k].box_int[0], dets[k].box_int[2]), 0);
             const int x2 = min(max(dets[k].box_int[0], dets[k].box_int[2]), a.w - 1);
@@ -171,22 +174,26 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
             sum += __shfl_xor_sync(0xffffffffu, sum, o);
             cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         }
-        if ((tid & 31) == 0 && cnt > 0) {
+        if (lane == 0 && cnt > 0) {
             atomicAdd((unsigned long long*)&s_envsum, (unsigned long long)sum);
             atomicAdd(&s_envcnt, cnt);
         }
     }
-    // ---- routing (measurement.py:249-272): ordered stitch list
-    if (tid == 0) {
+    // ---- routing (measurement.py:249-272): ordered stitch list, one warp, ballot compaction
+    if (tid < 32) {
         int ns = 0, nf = 0;
-        for (int k = 0; k < n; ++k) {
-            const unsigned f = dets[k].flags;
-            if (!(f & VTI_F_IN_ROI)) continue;
-            if (f & VTI_F_STITCH) s_st[ns++] = (short)k;
-            else if ((f & VTI_F_FABRIC) && ((f & VTI_F_HAS_MASK) || a.variant == 1)) ++nf;
+        for (int base = 0; base < n; base += 32) {
+            const int k = base + lane;
+            const unsigned f = k < n ? s_flags[k] : 0u;
+            const bool roi = f & VTI_F_IN_ROI;
+            const bool st = roi && (f & VTI_F_STITCH);
+            const bool fb = roi && !(f & VTI_F_STITCH) && (f & VTI_F_FABRIC) && ((f & VTI_F_HAS_MASK) || a.variant == 1);
+            const unsigned ms = __ballot_sync(0xffffffffu, st), mf = __ballot_sync(0xffffffffu, fb);
+            if (st) s_st[ns + __popc(ms & ((1u << lane) - 1u))] = (short)k;
+            ns += __popc(ms);
+            nf += __popc(mf);
         }
-        s_ns = ns;
-        s_nfab = nf;
+        if (lane == 0) { s_ns = ns; s_nfab = nf; }
     }
     __syncthreads();
     const int ns = s_ns;
@@ -214,9 +221,10 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         vti_det& d = dets[s_st[i]];
         double cx, cy, left, right;
         const int x1 = d.box_int[0], y1 = d.box_int[1], x2 = d.box_int[2], y2 = d.box_int[3];
-        if (d.m00 > 0) {
-            cx = (double)d.m10 / (double)d.m00;
-            cy = (double)d.m01 / (double)d.m00;
+        const long long m00 = d.m00;
+        if (m00 > 0) {
+            cx = (double)d.m10 / (double)m00;
+            cy = (double)d.m01 / (double)m00;
             left = (double)d.col_min;
             right = (double)d.col_max;
         } else {
@@ -227,9 +235,10 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         }
         d.cx = cx; d.cy = cy; d.left_px = left; d.right_px = right;
         s_cy[i] = cy;
+        s_w[i] = qnan;
         if (a.variant == 0) {
             double mm;
-            if (dist_mm(cam, left, cy, right, cy, &mm)) { d.width_mm = mm; d.flags |= VTI_F_HAS_WIDTH; }
+            if (dist_mm(cam, left, cy, right, cy, &mm)) { d.width_mm = mm; s_w[i] = mm; }
         }
     }
     __syncthreads();
@@ -307,48 +316,58 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     }
     __syncthreads();
     const int nfin = s_nfin;
-    for (int j = tid; j < nsel; j += K5_THREADS) dets[s_st[s_sel[j]]].flags |= VTI_F_SELECTED;
-    __syncthreads();                       // the same record gets VTI_F_FINAL from a different thread below
 
     // ---- edge distances (measurement.py:440-459) [+ widths of the final stitches, variant 1]
     for (int j = tid; j < nfin; j += K5_THREADS) {
-        vti_det& d = dets[s_st[s_fin[j]]];
-        d.flags |= VTI_F_FINAL;
+        const int i = s_fin[j];
+        vti_det& d = dets[s_st[i]];
         const int cx_int = min(max((int)rint(d.cx), 0), a.w - 1);
         double med, mm;
+        s_d[j] = qnan;
         if (env_median(envf, a.w, cx_int, a.nb, &med)) {
             d.edge_y = med;
-            if (dist_mm(cam, d.cx, d.cy, d.cx, med, &mm)) { d.dist_mm = mm; d.flags |= VTI_F_HAS_DIST; }
+            if (dist_mm(cam, d.cx, d.cy, d.cx, med, &mm)) { d.dist_mm = mm; s_d[j] = mm; }
         }
         if (a.variant == 1) {
             if (dist_mm(cam, d.left_px, d.cy, d.right_px, d.cy, &mm)) {
-                d.width_mm = mm; d.flags |= VTI_F_HAS_WIDTH;
+                d.width_mm = mm; s_w[i] = mm;
             } else if (dist_mm(cam, d.cx, d.cy, d.cx + 10.0, d.cy, &mm)) {
-                d.width_mm = ((d.right_px - d.left_px) / 10.0) * mm; d.flags |= VTI_F_HAS_WIDTH;
+                mm = ((d.right_px - d.left_px) / 10.0) * mm;
+                d.width_mm = mm; s_w[i] = mm;
             }
         }
     }
     __syncthreads();
+    // ---- record flags: one writer per detection
+    for (int j = tid; j < nsel; j += K5_THREADS) s_flags[s_st[s_sel[j]]] |= VTI_F_SELECTED;
+    __syncthreads();
+    for (int j = tid; j < nfin; j += K5_THREADS) {
+        unsigned f = VTI_F_FINAL;
+        if (s_d[j] == s_d[j]) f |= VTI_F_HAS_DIST;
+        s_flags[s_st[s_fin[j]]] |= f;
+    }
+    __syncthreads();
+    for (int i = tid; i < ns; i += K5_THREADS) {
+        unsigned f = s_flags[s_st[i]];
+        if (s_w[i] == s_w[i]) f |= VTI_F_HAS_WIDTH;
+        dets[s_st[i]].flags = f;
+    }
 
     // ---- averages (measurement.py:469-472), numpy summation order
     if (tid == 0) {
         int m = 0;
-        for (int j = 0; j < nfin; ++j) {
-            const vti_det& d = dets[s_st[s_fin[j]]];
-            if (d.flags & VTI_F_HAS_DIST) s_tmp[m++] = d.dist_mm;
-        }
+        for (int j = 0; j < nfin; ++j)
+            if (s_d[j] == s_d[j]) s_tmp[m++] = s_d[j];
         r.n_dist = m;
         if (m >= a.min_stitches) r.avg_dist = np_sum(s_tmp, m) / (double)m;
         m = 0;
         if (a.variant == 0) {
-            for (int i = 0; i < ns; ++i) {
-                const vti_det& d = dets[s_st[i]];
-                if (d.flags & VTI_F_HAS_WIDTH) s_tmp[m++] = d.width_mm;
-            }
+            for (int i = 0; i < ns; ++i)
+                if (s_w[i] == s_w[i]) s_tmp[m++] = s_w[i];
         } else {
             for (int j = 0; j < nfin; ++j) {
-                const vti_det& d = dets[s_st[s_fin[j]]];
-                if (d.flags & VTI_F_HAS_WIDTH) s_tmp[m++] = d.width_mm;
+                const double wv = s_w[s_fin[j]];
+                if (wv == wv) s_tmp[m++] = wv;
             }
         }
         r.n_width = m;

@@ -21,6 +21,10 @@ struct AxisLut {
     int32_t* sum;
     int32_t* first;   // INT_MAX when cnt == 0
     int32_t* last;    // -1 when cnt == 0
+    int32_t* pc;      // [n+1] prefix sums of cnt
+    int32_t* ps;      // [n+1] prefix sums of sum
+    int32_t* prev_last;   // max last[] over entries <= i (-1 if none)
+    int32_t* next_first;  // min first[] over entries >= i (INT_MAX if none)
 };
 
 struct vti_handle {
