@@ -13,6 +13,7 @@
 
 size_t vti_k3_smem_bytes(int cap);
 int vti_k3_prepare(int cap);
+int vti_k3_cap_pad(int cap);
 
 static thread_local std::string g_err;
 void vti_set_error(const std::string& s) { g_err = s; }
@@ -262,7 +263,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
     alloc((void**)&h->d_cand_count, sizeof(int32_t) * B);
-    alloc((void**)&h->d_cand_key, sizeof(unsigned long long) * B * g.max_candidates);
+    alloc((void**)&h->d_cand_key, sizeof(unsigned long long) * B * vti_k3_cap_pad(g.max_candidates));
     alloc((void**)&h->d_cand_box, sizeof(float4) * B * g.A);
     alloc((void**)&h->d_det_coef, sizeof(float) * B * p->max_det * VTI_NM);
     alloc((void**)&h->d_env, sizeof(int32_t) * B * g.LW);

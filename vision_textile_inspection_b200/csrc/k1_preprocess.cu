@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
     if (X >= a.LW) return;
     const int rx = X - a.left;
     const bool xin = (rx >= 0) && (rx < a.new_w);
-    int cs0 = 0, cs1 = 0, a0 = 0, a1 = 0;
+    int cs0 = 0, cs1 = 0;
+    unsigned a0 = 0, a1 = 0;
     if (xin && any) {
         if (col_contig) {
             const int sx = a.tap_x_idx[rx];
@@ -234,10 +235,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
             cs0 = 2 * (rx - rx_lo);
             cs1 = cs0 + 1;
         }
-        a0 = a.tap_x_a[2 * rx];
-        a1 = a.tap_x_a[2 * rx + 1];
+        a0 = (unsigned)a.tap_x_a[2 * rx];
+        a1 = (unsigned)a.tap_x_a[2 * rx + 1];
     }
     const size_t plane = (size_t)a.LH * a.LW;
+    const bool area = a.area2x != 0;
 #pragma unroll 2
     for (int i = 0; i < TY / 2; ++i) {
         const int j = (warp >> 2) * (TY / 2) + i;
@@ -250,17 +252,18 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
             const unsigned* row0 = s_und + rt.x * a.pitch_u;
             const unsigned* row1 = s_und + rt.y * a.pitch_u;
             const unsigned t00 = row0[cs0], t01 = row0[cs1], t10 = row1[cs0], t11 = row1[cs1];
-            int q[3];
+            const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
+            unsigned q[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const int p00 = (t00 >> (8 * ch)) & 255, p01 = (t01 >> (8 * ch)) & 255;
-                const int p10 = (t10 >> (8 * ch)) & 255, p11 = (t11 >> (8 * ch)) & 255;
-                if (a.area2x) {
-                    q[ch] = (p00 + p01 + p10 + p11 + 2) >> 2;
+                // all quantities are non-negative: unsigned shifts are single instructions
+                const unsigned p00 = (t00 >> (8 * ch)) & 255u, p01 = (t01 >> (8 * ch)) & 255u;
+                const unsigned p10 = (t10 >> (8 * ch)) & 255u, p11 = (t11 >> (8 * ch)) & 255u;
+                if (area) {
+                    q[ch] = (p00 + p01 + p10 + p11 + 2u) >> 2;
                 } else {
-                    const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
-                    const int o = (((rt.z * (S0 >> 4)) >> 16) + ((rt.w * (S1 >> 4)) >> 16) + 2) >> 2;
-                    q[ch] = min(max(o, 0), 255);
+                    const unsigned S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
+                    q[ch] = min(((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2u) >> 2), 255u);
                 }
             }
             v0 = s_div[q[0]]; v1 = s_div[q[1]]; v2 = s_div[q[2]];

@@ -12,6 +12,8 @@
 // key (score bits, ~anchor) which reproduces torchvision's stable descending sort over ascending anchor order.
 #include "vti_internal.h"
 
+int vti_k3_cap_pad(int cap);
+
 namespace {
 
 constexpr int K2_THREADS = 256;
@@ -20,7 +22,7 @@ struct K2Args {
     const float* lvl[3];
     int lvl_h[3], lvl_w[3];
     int a_begin[4];            // anchor offset of each level, a_begin[3] = A
-    int nc, A, cap;
+    int nc, A, cap, cap_pad;
     float conf;
     int32_t* cand_count;       // [B]
     unsigned long long* cand_key;   // [B][cap]
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_decode_kernel(const K2Args a) {
     if (slot < a.cap) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
                                        ((unsigned long long)(0xFFFFFFu - (unsigned)anchor) << 8) | (unsigned)cls;
-        a.cand_key[(size_t)b * a.cap + slot] = key;
+        a.cand_key[(size_t)b * a.cap_pad + slot] = key;
     }
 }
 
@@ -114,7 +116,7 @@ int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* 
         nblk += (a.lvl_h[l] * a.lvl_w[l] + K2_THREADS - 1) / K2_THREADS;
     }
     a.a_begin[3] = off;
-    a.nc = h->p.nc; a.A = h->g.A; a.cap = h->g.max_candidates;
+    a.nc = h->p.nc; a.A = h->g.A; a.cap = h->g.max_candidates; a.cap_pad = vti_k3_cap_pad(a.cap);
     a.conf = h->p.conf;
     a.cand_count = h->d_cand_count;
     a.cand_key = h->d_cand_key;

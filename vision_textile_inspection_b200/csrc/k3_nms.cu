@@ -24,6 +24,7 @@ namespace {
 constexpr int K3_THREADS = 1024;
 constexpr int CHUNK = 64;
 constexpr int MAX_DET_CAP = 1024;
+constexpr int KEYS_SMEM = 4096;     // sort buffer in shared memory; larger candidate sets sort in their global buffer
 
 struct K3Args {
     const int32_t* cand_count;
@@ -35,7 +36,7 @@ struct K3Args {
     float* det_coef;            // [B][max_det][32]
     int32_t* env;               // [B][LW]
     int32_t* flags;             // [B] : bit0 overflow, bits 8.. = n_cand
-    int cap, A, max_det, LW;
+    int cap, cap_pad, A, max_det, LW;
     double iou;
     float gain, padx, pady, fw, fh;
     int roi_active, rx1, ry1, rx2, ry2;
@@ -54,7 +55,7 @@ __device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4
 }
 
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];
+    extern __shared__ __align__(16) unsigned long long s_keys[];   // KEYS_SMEM entries
     __shared__ float4 s_kbox[MAX_DET_CAP];      // kept boxes (class offset applied)
     __shared__ float s_karea[MAX_DET_CAP];
     __shared__ int s_kidx[MAX_DET_CAP];         // sorted position of each kept box
@@ -71,24 +72,50 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     int n_pad = 64;
     while (n_pad < n) n_pad <<= 1;
 
-    const unsigned long long* __restrict__ gkeys = a.cand_key + (size_t)b * a.cap;
-    for (int i = tid; i < n_pad; i += K3_THREADS) s_keys[i] = (i < n) ? gkeys[i] : 0ull;
+    unsigned long long* gkeys = a.cand_key + (size_t)b * a.cap_pad;
+    unsigned long long* keys = (n_pad <= KEYS_SMEM) ? s_keys : gkeys;      // generic pointer: shared or global
     for (int i = tid; i < a.LW; i += K3_THREADS) a.env[(size_t)b * a.LW + i] = a.env_init;
     if (tid == 0) s_nk = 0;
-    __syncthreads();
 
     // ---- 1. bitonic sort, descending
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n_pad; i += K3_THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const unsigned long long x = s_keys[i], y = s_keys[p];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (x < y) : (x > y)) { s_keys[i] = y; s_keys[p] = x; }
+    if (n_pad <= K3_THREADS) {
+        // one key per thread in a register; partners closer than a warp come through shuffles, no barrier
+        unsigned long long key = (tid < n) ? gkeys[tid] : 0ull;
+        for (int k = 2; k <= n_pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long other;
+                if (j >= 32) {
+                    s_keys[tid] = key;
+                    __syncthreads();
+                    other = s_keys[tid ^ j];
+                    __syncthreads();
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, key, j);
                 }
+                const bool keep_max = (((tid & k) == 0) == ((tid & j) == 0));
+                key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
             }
-            __syncthreads();
+        }
+        s_keys[tid] = key;
+        __syncthreads();
+    } else {
+        for (int i = tid; i < n_pad; i += K3_THREADS) {
+            if (keys == s_keys) keys[i] = (i < n) ? gkeys[i] : 0ull;
+            else if (i >= n) keys[i] = 0ull;
+        }
+        __syncthreads();
+        for (int k = 2; k <= n_pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n_pad; i += K3_THREADS) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const unsigned long long x = keys[i], y = keys[p];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 
@@ -101,7 +128,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
             float ar = 0.f;
             if (i < n) {
-                const unsigned long long key = s_keys[i];
+                const unsigned long long key = keys[i];
                 const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
                 const float off = __fmul_rn((float)(int)(key & 0xFFull), 7680.0f);
                 const float4 r = gbox[anchor];
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     // ---- 3. epilogue
     vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
     if (tid < nk) {
-        const unsigned long long key = s_keys[s_kidx[tid]];
+        const unsigned long long key = keys[s_kidx[tid]];
         const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
         const int cls = (int)(key & 0xFFull);
         const float4 r = gbox[anchor];
@@ -204,7 +231,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     float* __restrict__ dc = a.det_coef + (size_t)b * a.max_det * VTI_NM;
     for (int i = tid; i < nk * VTI_NM; i += K3_THREADS) {
         const int k = i >> 5, c = i & 31;
-        const unsigned long long key = s_keys[s_kidx[k]];
+        const unsigned long long key = keys[s_kidx[k]];
         const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
         dc[i] = __ldg(coef + (size_t)c * a.A + anchor);
     }
@@ -216,10 +243,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
 
 }  // namespace
 
-size_t vti_k3_smem_bytes(int cap) {
+size_t vti_k3_smem_bytes(int) { return (size_t)KEYS_SMEM * sizeof(unsigned long long); }
+
+int vti_k3_cap_pad(int cap) {
     int n_pad = 64;
     while (n_pad < cap) n_pad <<= 1;
-    return (size_t)n_pad * sizeof(unsigned long long);
+    return n_pad;
 }
 
 int vti_k3_prepare(int cap) {
@@ -239,7 +268,7 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
     a.det_coef = h->d_det_coef;
     a.env = h->d_env;
     a.flags = h->d_flags;
-    a.cap = h->g.max_candidates; a.A = h->g.A; a.max_det = h->p.max_det; a.LW = h->g.LW;
+    a.cap = h->g.max_candidates; a.cap_pad = vti_k3_cap_pad(a.cap); a.A = h->g.A; a.max_det = h->p.max_det; a.LW = h->g.LW;
     a.iou = (double)h->p.iou;
     const int fh = h->p.frame_h, fw = h->p.frame_w, LH = h->g.LH, LW = h->g.LW;
     // ops.scale_boxes: gain/pad are Python doubles, the tensor math is float32 (oracle/post_spec.py scale_boxes_spec)

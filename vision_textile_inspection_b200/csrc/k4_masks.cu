@@ -110,14 +110,17 @@ __global__ void __launch_bounds__(K4_THREADS) k4_masks_kernel(const K4Args a) {
     const int nlist = s_nlist;
     if (nlist == 0) return;
 
-    // ---- stage the prototype footprint (replicate-clamped at the plane border)
+    // ---- stage the prototype footprint (replicate-clamped at the plane border): one thread per footprint pixel,
+    //      looping over the 32 channels, so the index arithmetic is done once per thread
     const int pr0 = (Y0 >> 2) - 1, pc0 = (X0 >> 2) - 1;
     const float* __restrict__ proto = a.proto + (size_t)b * VTI_NM * a.ph * a.pw;
-    for (int i = tid; i < VTI_NM * FP; i += K4_THREADS) {
-        const int k = i / FP, p = i - k * FP;
-        const int fr = p / FC, fc = p - fr * FC;
+    if (tid < FP) {
+        const int fr = tid / FC, fc = tid - fr * FC;
         const int py = min(max(pr0 + fr, 0), a.ph - 1), px = min(max(pc0 + fc, 0), a.pw - 1);
-        s_proto[k][p] = __ldg(proto + ((size_t)k * a.ph + py) * a.pw + px);
+        const float* __restrict__ src = proto + (size_t)py * a.pw + px;
+        const size_t plane = (size_t)a.ph * a.pw;
+#pragma unroll 8
+        for (int k = 0; k < VTI_NM; ++k) s_proto[k][tid] = __ldg(src + k * plane);
     }
 
     // this thread's footprint pixel (phase 1) and interpolation cell (phase 2)
