@@ -169,7 +169,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
-                    h->d_counts, h->d_results, h->d_k1_tiles};
+                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -30,7 +30,7 @@ constexpr int TY = VTI_K1_TY;
 constexpr int K1_THREADS = 256;
 constexpr int MAXROWS = 2 * TY + 2;
 constexpr int MAXCOLS = 2 * TX + 2;
-enum { MODE_PLAIN = 0, MODE_RAW = 1, MODE_GATHER = 2 };
+enum { MODE_PLAIN = 0, MODE_RAW = 1, MODE_GATHER = 2, MODE_FAST_PLAIN = 3, MODE_FAST_REMAP = 4 };
 
 struct K1Args {
     const uint8_t* frames;
@@ -275,16 +275,298 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
     }
 }
 
+
+// ====================================================================================================================
+// Fast path (v3): frame width % 4 == 0 and every tile's source footprint contiguous (shrink < 2x, or upscale).
+//
+// The ALU pipe (LOP3/SHF/PRMT, 0.5 warp-inst/clk/SMSP) bounded v2, so v3 is organised around instruction count:
+//   * the remap table is PER TILE and pre-resolved on the host: entry = shared-memory byte offset of the 2x2 raw
+//     neighbourhood | fy << 8 | fx.  Out-of-image taps point into a zero margin staged around the raw box, so the
+//     inner loop has no bounds logic.  The table is read linearly (coalesced) and is L2-resident across the batch.
+//   * remap math: per channel, PRMT builds (p_x | p_x+1 << 16) for both rows, two IMADs blend the rows for both
+//     columns at once, one IDP.2A (dp2a) does the column blend + rounding constant: 2 PRMT + 2 IMAD + 1 IDP + 1 SHF.
+//   * resize math: PRMT pairs the two horizontal taps of two channels, IDP.2A applies the 11-bit (a0, a1) taps;
+//     the V pass multiplies by (b0, b1), PRMT extracts both >>16 at once and IDP.2A adds them with the +2.
+// ====================================================================================================================
+constexpr int FT_THREADS = 256;
+
+struct K1FastArgs {
+    const uint8_t* frames;
+    float* out;
+    const int4* tile_hdr;       // [tiles][2]: (bx0, by0, bw, bh), (r_lo, c_lo, nrows, ncols)
+    const unsigned* lut;        // [tiles][rows_u * pitch_u]   (REMAP only)
+    const int32_t* tap_x_idx;   // [new_w]
+    const int16_t* tap_x_a;     // [new_w][2]
+    const int32_t* tap_y_i;     // [new_h][2]
+    const int16_t* tap_y_b;     // [new_h][2]
+    int h, w, new_h, new_w, top, left, LH, LW;
+    int area2x, flip;
+    int pitch_u, rows_u;
+};
+
+// Stage rows [y0, y0+nr) x 4-pixel groups [x0, x0 + 4*ng) of the frame as packed words; anything outside the image
+// becomes 0 (the zero margin of cv2.remap's BORDER_CONSTANT).  x0 % 4 == 0 and w % 4 == 0.
+__device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
+                                          unsigned* dst, int tid, int flip) {
+    const int total = ng * nr;
+    for (int i = tid; i < total; i += FT_THREADS) {
+        const int r = i / ng, g = i - r * ng;
+        const int y = y0 + r, x = x0 + 4 * g;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) {
+            const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(frame + ((size_t)y * w + x) * 3);
+            const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+            v.x = w0 & 0xFFFFFFu;
+            v.y = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
+            v.z = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
+            v.w = w2 >> 8;
+            if (flip) {
+                v.x = __byte_perm(v.x, 0, 0x3012); v.y = __byte_perm(v.y, 0, 0x3012);
+                v.z = __byte_perm(v.z, 0, 0x3012); v.w = __byte_perm(v.w, 0, 0x3012);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst + 4 * i) = v;
+    }
+}
+
+__device__ __forceinline__ unsigned remap_fast(const unsigned char* raw, unsigned e, unsigned bw4) {
+    const unsigned off = e >> 16;
+    const unsigned fx = e & 0xFFu, fy = __byte_perm(e, 0, 0x4441);
+    const unsigned t00 = *reinterpret_cast<const unsigned*>(raw + off);
+    const unsigned t01 = *reinterpret_cast<const unsigned*>(raw + off + 4);
+    const unsigned t10 = *reinterpret_cast<const unsigned*>(raw + off + bw4);
+    const unsigned t11 = *reinterpret_cast<const unsigned*>(raw + off + bw4 + 4);
+    const unsigned wy0 = 32u - fy;
+    const unsigned wxb = fx * 255u + 32u;                      // (32 - fx) | fx << 8
+    // rows blended for both columns at once: (V_x | V_x+1 << 16), each <= 8160
+    const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
+    const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
+    const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
+    const unsigned b = __dp2a_lo(vB, wxb, 512u) >> 10;
+    const unsigned g = __dp2a_lo(vG, wxb, 512u) >> 10;
+    const unsigned r = __dp2a_lo(vR, wxb, 512u) >> 10;
+    return r * 65536u + (g * 256u + b);
+}
+
+template <bool REMAP>
+__global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a) {
+    extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [rows_u][pitch_u], then the raw box (REMAP)
+    __shared__ float s_div[256];
+    __shared__ int4 s_rowtap[TY];                          // (byte offset row0, byte offset row1, b0, b1)
+
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
+    const int b = blockIdx.z;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const uint8_t* __restrict__ frame = a.frames + (size_t)b * a.h * a.w * 3;
+    float* __restrict__ out = a.out + (size_t)b * 3 * a.LH * a.LW;
+    unsigned* s_und = s_dyn;
+
+    const int4 h0 = __ldg(a.tile_hdr + 2 * tile), h1 = __ldg(a.tile_hdr + 2 * tile + 1);
+    const int r_lo = h1.x, c_lo = h1.y, nrows = h1.z;
+    s_div[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (tid < TY) {
+        const int ry = Y0 + tid - a.top;
+        int4 t = make_int4(0, 0, 0, 0);
+        if (ry >= 0 && ry < a.new_h && nrows > 0) {
+            t.x = (a.tap_y_i[2 * ry] - r_lo) * a.pitch_u * 4;
+            t.y = (a.tap_y_i[2 * ry + 1] - r_lo) * a.pitch_u * 4;
+            t.z = a.tap_y_b[2 * ry];
+            t.w = a.tap_y_b[2 * ry + 1];
+        }
+        s_rowtap[tid] = t;
+    }
+
+    // ------------------------------------------------------------------------------------------- stage (+ remap)
+    if (nrows > 0) {
+        if (!REMAP) {
+            stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 2, nrows, s_und, tid, a.flip);
+        } else {
+            unsigned* s_raw = s_dyn + a.rows_u * a.pitch_u;
+            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 2, h0.w, s_raw, tid, a.flip);
+            __syncthreads();
+            const unsigned char* raw = reinterpret_cast<const unsigned char*>(s_raw);
+            const unsigned bw4 = (unsigned)h0.z * 4u;
+            const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.rows_u * a.pitch_u;
+            const int n_e = nrows * a.pitch_u;
+            int i = tid;
+            for (; i + 3 * FT_THREADS < n_e; i += 4 * FT_THREADS) {
+                const unsigned e0 = __ldg(lut + i), e1 = __ldg(lut + i + FT_THREADS);
+                const unsigned e2 = __ldg(lut + i + 2 * FT_THREADS), e3 = __ldg(lut + i + 3 * FT_THREADS);
+                s_und[i] = remap_fast(raw, e0, bw4);
+                s_und[i + FT_THREADS] = remap_fast(raw, e1, bw4);
+                s_und[i + 2 * FT_THREADS] = remap_fast(raw, e2, bw4);
+                s_und[i + 3 * FT_THREADS] = remap_fast(raw, e3, bw4);
+            }
+            for (; i < n_e; i += FT_THREADS) s_und[i] = remap_fast(raw, __ldg(lut + i), bw4);
+        }
+    }
+    __syncthreads();
+
+    // ----------------------------------------------------------------------------------------------- resize
+    const float pad = s_div[114];
+    const int X = X0 + (tid & (TX - 1));
+    if (X >= a.LW) return;
+    const int rx = X - a.left;
+    const bool xin = (rx >= 0) && (rx < a.new_w) && (nrows > 0);
+    unsigned cs0 = 0, cs1 = 0, a01 = 0;
+    if (xin) {
+        const int sx = a.tap_x_idx[rx];
+        cs0 = (unsigned)(sx - c_lo) * 4u;
+        cs1 = (unsigned)(min(sx + 1, a.w - 1) - c_lo) * 4u;
+        a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
+    }
+    const size_t plane = (size_t)a.LH * a.LW;
+    const bool area = a.area2x != 0;
+    const unsigned char* und = reinterpret_cast<const unsigned char*>(s_und);
+    const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
+    constexpr int RPT = TY / (FT_THREADS / TX);            // rows per thread
+    const int j0 = (tid / TX) * RPT;
+    float* o = out + (size_t)(Y0 + j0) * a.LW + X;
+#pragma unroll 4
+    for (int i = 0; i < RPT; ++i, o += a.LW) {
+        const int j = j0 + i;
+        if (Y0 + j >= a.LH) break;
+        const int ry = Y0 + j - a.top;
+        float v0 = pad, v1 = pad, v2 = pad;
+        if (xin && ry >= 0 && ry < a.new_h) {
+            const int4 rt = s_rowtap[j];
+            const unsigned t00 = *reinterpret_cast<const unsigned*>(und + rt.x + cs0);
+            const unsigned t01 = *reinterpret_cast<const unsigned*>(und + rt.x + cs1);
+            const unsigned t10 = *reinterpret_cast<const unsigned*>(und + rt.y + cs0);
+            const unsigned t11 = *reinterpret_cast<const unsigned*>(und + rt.y + cs1);
+            const unsigned bg0 = __byte_perm(t00, t01, 0x5140), rr0 = __byte_perm(t00, t01, 0x3362);
+            const unsigned bg1 = __byte_perm(t10, t11, 0x5140), rr1 = __byte_perm(t10, t11, 0x3362);
+            const unsigned S0b = __dp2a_lo(a01, bg0, 0u), S0g = __dp2a_hi(a01, bg0, 0u), S0r = __dp2a_lo(a01, rr0, 0u);
+            const unsigned S1b = __dp2a_lo(a01, bg1, 0u), S1g = __dp2a_hi(a01, bg1, 0u), S1r = __dp2a_lo(a01, rr1, 0u);
+            unsigned qb, qg, qr;             // 4 * quantised value (+ 0..3): the byte offset into s_div after & ~3
+            if (area) {
+                qb = S0b + S1b + 2u; qg = S0g + S1g + 2u; qr = S0r + S1r + 2u;
+            } else {
+                const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
+                qb = __dp2a_lo(__byte_perm(b0 * (S0b >> 4), b1 * (S1b >> 4), 0x7632), 0x0101u, 2u);
+                qg = __dp2a_lo(__byte_perm(b0 * (S0g >> 4), b1 * (S1g >> 4), 0x7632), 0x0101u, 2u);
+                qr = __dp2a_lo(__byte_perm(b0 * (S0r >> 4), b1 * (S1r >> 4), 0x7632), 0x0101u, 2u);
+            }
+            v0 = *reinterpret_cast<const float*>(divb + (min(qb, 1023u) & ~3u));
+            v1 = *reinterpret_cast<const float*>(divb + (min(qg, 1023u) & ~3u));
+            v2 = *reinterpret_cast<const float*>(divb + (min(qr, 1023u) & ~3u));
+        }
+        o[0] = v0;
+        o[plane] = v1;
+        o[2 * plane] = v2;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host plan
 // Mirrors the kernel's per-tile footprint logic to size the shared buffers and, with undistort on, to find the
 // raw-frame bounding box of every tile's remap taps.
+// Fast-path plan: per-tile headers and (undistort) the per-tile pre-resolved remap table.  Returns false when the
+// geometry is not eligible (the generic kernel below takes over).
+static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                         const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy,
+                         std::vector<int4>& hdr, std::vector<unsigned>& lut, int& pitch_u, int& rows_u, size_t& raw_words) {
+    const vti_geometry& g = h->g;
+    const int fw = h->p.frame_w, fh = h->p.frame_h;
+    if (fw & 3) return false;
+    const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
+    hdr.assign((size_t)ntx * nty * 2, make_int4(0, 0, 0, 0));
+    pitch_u = 4; rows_u = 1; raw_words = 0;
+    // pass 1: footprints
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+            const int X0 = tx * TX, Y0 = ty * TY;
+            const int ry_lo = std::max(Y0 - g.top, 0), ry_hi = std::min(Y0 + TY - 1 - g.top, g.new_h - 1);
+            const int rx_lo = std::max(X0 - g.left, 0), rx_hi = std::min(X0 + TX - 1 - g.left, g.new_w - 1);
+            if (ry_lo > ry_hi || rx_lo > rx_hi) continue;                     // pure padding tile: nrows = 0
+            int r_lo = INT32_MAX, r_hi = -1, c_lo = INT32_MAX, c_hi = -1;
+            for (int ry = ry_lo; ry <= ry_hi; ++ry) {
+                r_lo = std::min(r_lo, std::min(yi[2 * ry], yi[2 * ry + 1]));
+                r_hi = std::max(r_hi, std::max(yi[2 * ry], yi[2 * ry + 1]));
+            }
+            for (int rx = rx_lo; rx <= rx_hi; ++rx) {
+                c_lo = std::min(c_lo, xi[rx]);
+                c_hi = std::max(c_hi, std::min(xi[rx] + 1, fw - 1));
+            }
+            c_lo &= ~3;
+            const int nrows = r_hi - r_lo + 1, ncols = c_hi - c_lo + 1;
+            if (nrows > MAXROWS || ncols > MAXCOLS + 4) return false;
+            rows_u = std::max(rows_u, nrows);
+            pitch_u = std::max(pitch_u, (ncols + 3) & ~3);
+            hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
+        }
+    if (!und_ix) return true;
+    // pass 2: raw boxes + remap entries
+    lut.assign((size_t)ntx * nty * rows_u * pitch_u, 0u);
+    for (size_t t = 0; t < (size_t)ntx * nty; ++t) {
+        const int4 f = hdr[2 * t + 1];
+        const int r_lo = f.x, c_lo = f.y, nrows = f.z;
+        if (nrows == 0) continue;
+        const int c_end = std::min(c_lo + pitch_u, fw);            // remap every staged column that exists
+        int minx = INT32_MAX, miny = INT32_MAX, maxx = INT32_MIN, maxy = INT32_MIN;
+        auto clampx = [&](int x) { return x < -1 ? -2 : (x > fw - 1 ? fw : x); };
+        auto clampy = [&](int y) { return y < -1 ? -2 : (y > fh - 1 ? fh : y); };
+        for (int sy = r_lo; sy < r_lo + nrows; ++sy)
+            for (int sx = c_lo; sx < c_end; ++sx) {
+                const size_t i = (size_t)sy * fw + sx;
+                const int x = clampx((*und_ix)[i] >> 5), y = clampy((*und_iy)[i] >> 5);
+                minx = std::min(minx, x); maxx = std::max(maxx, x);
+                miny = std::min(miny, y); maxy = std::max(maxy, y);
+            }
+        const int bx0 = (minx >= 0) ? (minx & ~3) : -4;
+        const int bx1 = (maxx + 2 + 3) & ~3;                        // exclusive, covers x + 1
+        const int bw = bx1 - bx0, by0 = miny, bh = maxy + 2 - miny;
+        if ((size_t)bw * bh > 16384) return false;                  // 16-bit byte offsets
+        raw_words = std::max(raw_words, (size_t)bw * bh);
+        hdr[2 * t] = make_int4(bx0, by0, bw, bh);
+        unsigned* L = lut.data() + t * rows_u * pitch_u;
+        for (int r = 0; r < nrows; ++r)
+            for (int c = 0; c < pitch_u; ++c) {
+                const int sy = r_lo + r, sx = c_lo + c;
+                unsigned e = 0u;                                    // columns past the frame: any valid cell
+                if (sx < fw) {
+                    const size_t i = (size_t)sy * fw + sx;
+                    const int ix = (*und_ix)[i], iy = (*und_iy)[i];
+                    const int x = clampx(ix >> 5), y = clampy(iy >> 5);
+                    const unsigned off = (unsigned)(((y - by0) * bw + (x - bx0)) * 4);
+                    e = (off << 16) | ((unsigned)(iy & 31) << 8) | (unsigned)(ix & 31);
+                }
+                L[(size_t)r * pitch_u + c] = e;
+            }
+    }
+    return true;
+}
+
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
                 const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy) {
     const vti_geometry& g = h->g;
     const int fw = h->p.frame_w, fh = h->p.frame_h;
     const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
+    {
+        std::vector<int4> hdr;
+        std::vector<unsigned> lut;
+        int pitch_u = 0, rows_u = 0;
+        size_t raw_words = 0;
+        if (k1_fast_plan(h, xi, yi, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words)) {
+            const size_t smem = ((size_t)rows_u * pitch_u + raw_words) * 4;
+            if (smem <= 100 * 1024) {
+                h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
+                h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;
+                VTI_CUDA(cudaMalloc((void**)&h->d_k1_tiles, sizeof(int4) * hdr.size()));
+                VTI_CUDA(cudaMemcpy(h->d_k1_tiles, hdr.data(), sizeof(int4) * hdr.size(), cudaMemcpyHostToDevice));
+                if (und_ix) {
+                    VTI_CUDA(cudaMalloc((void**)&h->d_k1_lut, sizeof(unsigned) * lut.size()));
+                    VTI_CUDA(cudaMemcpy(h->d_k1_lut, lut.data(), sizeof(unsigned) * lut.size(), cudaMemcpyHostToDevice));
+                    VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                } else {
+                    VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                }
+                return VTI_OK;
+            }
+        }
+    }
     int ncols_max = 4, nrows_max = 1;
     bool all_contig = true;
     std::vector<int4> boxes((size_t)ntx * nty, make_int4(0, 0, 0, 0));
@@ -363,6 +645,22 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
 }
 
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s) {
+    if (h->k1_mode == MODE_FAST_PLAIN || h->k1_mode == MODE_FAST_REMAP) {
+        K1FastArgs f;
+        f.frames = frames; f.out = net_in;
+        f.tile_hdr = h->d_k1_tiles; f.lut = h->d_k1_lut;
+        f.tap_x_idx = h->d_tap_x_idx; f.tap_x_a = h->d_tap_x_a; f.tap_y_i = h->d_tap_y_i; f.tap_y_b = h->d_tap_y_b;
+        f.h = h->p.frame_h; f.w = h->p.frame_w; f.new_h = h->g.new_h; f.new_w = h->g.new_w;
+        f.top = h->g.top; f.left = h->g.left; f.LH = h->g.LH; f.LW = h->g.LW;
+        f.area2x = (h->resize_mode == 2); f.flip = h->p.channel_flip;
+        f.pitch_u = h->k1_pitch_u; f.rows_u = h->k1_rows_u;
+        dim3 grid((f.LW + TX - 1) / TX, (f.LH + TY - 1) / TY, B);
+        if (h->k1_mode == MODE_FAST_REMAP) k1_fast_kernel<true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        else k1_fast_kernel<false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        h->launches++;
+        VTI_CUDA(cudaGetLastError());
+        return VTI_OK;
+    }
     K1Args a;
     a.frames = frames;
     a.out = net_in;

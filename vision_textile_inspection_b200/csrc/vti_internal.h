@@ -41,7 +41,8 @@ struct vti_handle {
     int resize_mode;                               // 1 bilinear (incl. identity taps), 2 exact-2x area
     int k1_mode, k1_pitch_u, k1_rows_u;            // staging mode + shared footprint buffer shape (k1 plan)
     size_t k1_smem;
-    int4* d_k1_tiles;                              // per-tile raw bounding boxes (undistort, MODE_RAW)
+    int4* d_k1_tiles;                              // per-tile headers (fast path) / raw bounding boxes (MODE_RAW)
+    unsigned* d_k1_lut;                            // per-tile pre-resolved remap entries (fast path, undistort)
     // ---- measurement tables (device)
     AxisLut lutY, lutX;                            // [LH], [LW]
     int32_t* d_xmap;                               // [frame_w] frame col -> letterbox col
