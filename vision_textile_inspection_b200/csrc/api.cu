@@ -248,7 +248,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
                 }
             if ((rc = upload(&h->d_und_lut, packed))) { vti_destroy(h); return rc; }
         }
-        if ((rc = vti_k1_plan(h, xi, yi, p->undistort ? &ix : nullptr, p->undistort ? &iy : nullptr))) {
+        if ((rc = vti_k1_plan(h, xi, yi, xa, yb, p->undistort ? &ix : nullptr, p->undistort ? &iy : nullptr))) {
             vti_destroy(h);
             return rc;
         }

@@ -289,19 +289,22 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 //     the V pass multiplies by (b0, b1), PRMT extracts both >>16 at once and IDP.2A adds them with the +2.
 // ====================================================================================================================
 constexpr int FT_THREADS = 256;
+constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration
 
 struct K1FastArgs {
     const uint8_t* frames;
     float* out;
     const int4* tile_hdr;       // [tiles][2]: (bx0, by0, bw, bh), (r_lo, c_lo, nrows, ncols)
-    const unsigned* lut;        // [tiles][rows_u * pitch_u]   (REMAP only)
+    const unsigned* lut;        // [tiles][lut_stride]   (REMAP only)
     const int32_t* tap_x_idx;   // [new_w]
     const int16_t* tap_x_a;     // [new_w][2]
     const int32_t* tap_y_i;     // [new_h][2]
     const int16_t* tap_y_b;     // [new_h][2]
     int h, w, new_h, new_w, top, left, LH, LW;
-    int area2x, flip;
+    int flip;
     int pitch_u, rows_u;
+    int und_words;              // words reserved for the footprint buffer (multiple of FT_CHUNK, > rows_u * pitch_u)
+    int lut_stride;             // entries per tile (multiple of FT_CHUNK)
 };
 
 // Stage rows [y0, y0+nr) x 4-pixel groups [x0, x0 + 4*ng) of the frame as packed words; anything outside the image
@@ -309,8 +312,12 @@ struct K1FastArgs {
 __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
                                           unsigned* dst, int tid, int flip) {
     const int total = ng * nr;
+    const float inv_ng = 1.0f / (float)ng;
+#pragma unroll 2
     for (int i = tid; i < total; i += FT_THREADS) {
-        const int r = i / ng, g = i - r * ng;
+        // i / ng for i < 2^14, ng <= 2^8: (i + 0.5) / ng is never within 1/(2 ng) of an integer, far above fp32 error
+        const int r = (int)(((float)i + 0.5f) * inv_ng);
+        const int g = i - r * ng;
         const int y = y0 + r, x = x0 + 4 * g;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) {
@@ -336,21 +343,54 @@ __device__ __forceinline__ unsigned remap_fast(const unsigned char* raw, unsigne
     const unsigned t01 = *reinterpret_cast<const unsigned*>(raw + off + 4);
     const unsigned t10 = *reinterpret_cast<const unsigned*>(raw + off + bw4);
     const unsigned t11 = *reinterpret_cast<const unsigned*>(raw + off + bw4 + 4);
-    const unsigned wy0 = 32u - fy;
+    const unsigned wy0 = fy * 0xFFFFFFFFu + 32u;               // 32 - fy, as a multiply-add (FMA pipe)
     const unsigned wxb = fx * 255u + 32u;                      // (32 - fx) | fx << 8
     // rows blended for both columns at once: (V_x | V_x+1 << 16), each <= 8160
     const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
     const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
     const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
-    const unsigned b = __dp2a_lo(vB, wxb, 512u) >> 10;
-    const unsigned g = __dp2a_lo(vG, wxb, 512u) >> 10;
-    const unsigned r = __dp2a_lo(vR, wxb, 512u) >> 10;
-    return r * 65536u + (g * 256u + b);
+    // (acc + 512) >> 10 is an 8-bit value; << 6 parks it in byte 2 where PRMT can pick it up
+    const unsigned b = __dp2a_lo(vB, wxb, 512u) * 64u;
+    const unsigned g = __dp2a_lo(vG, wxb, 512u) * 64u;
+    const unsigned r = __dp2a_lo(vR, wxb, 512u) * 64u;
+    return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);           // bytes 3 of b, g, r are 0
 }
 
-template <bool REMAP>
+// base[idx] = v with the address formed by ONE mad.wide (FMA pipe) -- the compiler's own 64-bit index arithmetic
+// costs four ALU-pipe instructions per store, and the ALU pipe is what bounds this kernel.
+__device__ __forceinline__ void store_at(float* base, int idx, float v) {
+    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}"
+                 :: "l"(base), "r"(idx), "f"(v) : "memory");
+}
+
+// One output pixel (3 channels) of cv2.resize's fixed-point bilinear (or the exact-2x area average) + /255.
+template <bool AREA>
+__device__ __forceinline__ void resize_px(const unsigned char* p0, const unsigned char* p1, unsigned a01, unsigned b0,
+                                          unsigned b1, const unsigned char* divb, float& v0, float& v1, float& v2) {
+    const unsigned t00 = *reinterpret_cast<const unsigned*>(p0), t01 = *reinterpret_cast<const unsigned*>(p0 + 4);
+    const unsigned t10 = *reinterpret_cast<const unsigned*>(p1), t11 = *reinterpret_cast<const unsigned*>(p1 + 4);
+    const unsigned bg0 = __byte_perm(t00, t01, 0x5140), rr0 = __byte_perm(t00, t01, 0x3362);
+    const unsigned bg1 = __byte_perm(t10, t11, 0x5140), rr1 = __byte_perm(t10, t11, 0x3362);
+    const unsigned S0b = __dp2a_lo(a01, bg0, 0u), S0g = __dp2a_hi(a01, bg0, 0u), S0r = __dp2a_lo(a01, rr0, 0u);
+    unsigned qb, qg, qr;                     // 4 * quantised value + (0..3): the byte offset into s_div after & ~3
+    if (AREA) {
+        qb = __dp2a_lo(a01, bg1, S0b + 2u); qg = __dp2a_hi(a01, bg1, S0g + 2u); qr = __dp2a_lo(a01, rr1, S0r + 2u);
+    } else {
+        const unsigned S1b = __dp2a_lo(a01, bg1, 0u), S1g = __dp2a_hi(a01, bg1, 0u), S1r = __dp2a_lo(a01, rr1, 0u);
+        // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2: PRMT takes both >> 16 at once, dp2a adds them.
+        // The plan guarantees a0 + a1 <= 2049 and b0 + b1 <= 2049, so the sum is <= 1022: no saturation needed.
+        qb = __dp2a_lo(__byte_perm(b0 * (S0b >> 4), b1 * (S1b >> 4), 0x7632), 0x0101u, 2u);
+        qg = __dp2a_lo(__byte_perm(b0 * (S0g >> 4), b1 * (S1g >> 4), 0x7632), 0x0101u, 2u);
+        qr = __dp2a_lo(__byte_perm(b0 * (S0r >> 4), b1 * (S1r >> 4), 0x7632), 0x0101u, 2u);
+    }
+    v0 = *reinterpret_cast<const float*>(divb + (qb & 0x3FCu));
+    v1 = *reinterpret_cast<const float*>(divb + (qg & 0x3FCu));
+    v2 = *reinterpret_cast<const float*>(divb + (qr & 0x3FCu));
+}
+
+template <bool REMAP, bool AREA>
 __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a) {
-    extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [rows_u][pitch_u], then the raw box (REMAP)
+    extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [und_words], then the raw box (REMAP)
     __shared__ float s_div[256];
     __shared__ int4 s_rowtap[TY];                          // (byte offset row0, byte offset row1, b0, b1)
 
@@ -382,23 +422,20 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
         if (!REMAP) {
             stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 2, nrows, s_und, tid, a.flip);
         } else {
-            unsigned* s_raw = s_dyn + a.rows_u * a.pitch_u;
+            unsigned* s_raw = s_dyn + a.und_words;
             stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 2, h0.w, s_raw, tid, a.flip);
             __syncthreads();
             const unsigned char* raw = reinterpret_cast<const unsigned char*>(s_raw);
             const unsigned bw4 = (unsigned)h0.z * 4u;
-            const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.rows_u * a.pitch_u;
-            const int n_e = nrows * a.pitch_u;
-            int i = tid;
-            for (; i + 3 * FT_THREADS < n_e; i += 4 * FT_THREADS) {
-                const unsigned e0 = __ldg(lut + i), e1 = __ldg(lut + i + FT_THREADS);
-                const unsigned e2 = __ldg(lut + i + 2 * FT_THREADS), e3 = __ldg(lut + i + 3 * FT_THREADS);
-                s_und[i] = remap_fast(raw, e0, bw4);
-                s_und[i + FT_THREADS] = remap_fast(raw, e1, bw4);
-                s_und[i + 2 * FT_THREADS] = remap_fast(raw, e2, bw4);
-                s_und[i + 3 * FT_THREADS] = remap_fast(raw, e3, bw4);
+            const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
+            unsigned* dst = s_und + tid;
+            const int n_it = (nrows * a.pitch_u + FT_CHUNK - 1) / FT_CHUNK;     // table and buffer are padded
+#pragma unroll 2
+            for (int it = 0; it < n_it; ++it, lut += FT_CHUNK, dst += FT_CHUNK) {
+                const unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
+                dst[0] = remap_fast(raw, e0, bw4);
+                dst[FT_THREADS] = remap_fast(raw, e1, bw4);
             }
-            for (; i < n_e; i += FT_THREADS) s_und[i] = remap_fast(raw, __ldg(lut + i), bw4);
         }
     }
     __syncthreads();
@@ -407,54 +444,44 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
     const float pad = s_div[114];
     const int X = X0 + (tid & (TX - 1));
     if (X >= a.LW) return;
-    const int rx = X - a.left;
-    const bool xin = (rx >= 0) && (rx < a.new_w) && (nrows > 0);
-    unsigned cs0 = 0, cs1 = 0, a01 = 0;
-    if (xin) {
-        const int sx = a.tap_x_idx[rx];
-        cs0 = (unsigned)(sx - c_lo) * 4u;
-        cs1 = (unsigned)(min(sx + 1, a.w - 1) - c_lo) * 4u;
-        a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
-    }
-    const size_t plane = (size_t)a.LH * a.LW;
-    const bool area = a.area2x != 0;
-    const unsigned char* und = reinterpret_cast<const unsigned char*>(s_und);
-    const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
     constexpr int RPT = TY / (FT_THREADS / TX);            // rows per thread
     const int j0 = (tid / TX) * RPT;
-    float* o = out + (size_t)(Y0 + j0) * a.LW + X;
-#pragma unroll 4
-    for (int i = 0; i < RPT; ++i, o += a.LW) {
-        const int j = j0 + i;
-        if (Y0 + j >= a.LH) break;
-        const int ry = Y0 + j - a.top;
-        float v0 = pad, v1 = pad, v2 = pad;
-        if (xin && ry >= 0 && ry < a.new_h) {
-            const int4 rt = s_rowtap[j];
-            const unsigned t00 = *reinterpret_cast<const unsigned*>(und + rt.x + cs0);
-            const unsigned t01 = *reinterpret_cast<const unsigned*>(und + rt.x + cs1);
-            const unsigned t10 = *reinterpret_cast<const unsigned*>(und + rt.y + cs0);
-            const unsigned t11 = *reinterpret_cast<const unsigned*>(und + rt.y + cs1);
-            const unsigned bg0 = __byte_perm(t00, t01, 0x5140), rr0 = __byte_perm(t00, t01, 0x3362);
-            const unsigned bg1 = __byte_perm(t10, t11, 0x5140), rr1 = __byte_perm(t10, t11, 0x3362);
-            const unsigned S0b = __dp2a_lo(a01, bg0, 0u), S0g = __dp2a_hi(a01, bg0, 0u), S0r = __dp2a_lo(a01, rr0, 0u);
-            const unsigned S1b = __dp2a_lo(a01, bg1, 0u), S1g = __dp2a_hi(a01, bg1, 0u), S1r = __dp2a_lo(a01, rr1, 0u);
-            unsigned qb, qg, qr;             // 4 * quantised value (+ 0..3): the byte offset into s_div after & ~3
-            if (area) {
-                qb = S0b + S1b + 2u; qg = S0g + S1g + 2u; qr = S0r + S1r + 2u;
-            } else {
-                const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
-                qb = __dp2a_lo(__byte_perm(b0 * (S0b >> 4), b1 * (S1b >> 4), 0x7632), 0x0101u, 2u);
-                qg = __dp2a_lo(__byte_perm(b0 * (S0g >> 4), b1 * (S1g >> 4), 0x7632), 0x0101u, 2u);
-                qr = __dp2a_lo(__byte_perm(b0 * (S0r >> 4), b1 * (S1r >> 4), 0x7632), 0x0101u, 2u);
-            }
-            v0 = *reinterpret_cast<const float*>(divb + (min(qb, 1023u) & ~3u));
-            v1 = *reinterpret_cast<const float*>(divb + (min(qg, 1023u) & ~3u));
-            v2 = *reinterpret_cast<const float*>(divb + (min(qr, 1023u) & ~3u));
+    const size_t plane = (size_t)a.LH * a.LW;
+    float* __restrict__ o0 = out + (size_t)(Y0 + j0) * a.LW + X;     // three plane pointers + one 32-bit row offset
+    float* __restrict__ o1 = o0 + plane;
+    float* __restrict__ o2 = o1 + plane;
+    int oi = 0;
+    const int rx = X - a.left;
+    if (rx < 0 || rx >= a.new_w || nrows == 0) {           // padding column
+#pragma unroll
+        for (int i = 0; i < RPT; ++i, oi += a.LW) {
+            store_at(o0, oi, pad); store_at(o1, oi, pad); store_at(o2, oi, pad);
         }
-        o[0] = v0;
-        o[plane] = v1;
-        o[2 * plane] = v2;
+        return;
+    }
+    const int sx = a.tap_x_idx[rx];
+    const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
+    const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
+    const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
+    const int ry0 = Y0 + j0 - a.top;
+    if (ry0 >= 0 && ry0 + RPT <= a.new_h) {                // no padding rows in this thread's strip (warp-uniform)
+#pragma unroll 4
+        for (int i = 0; i < RPT; ++i, oi += a.LW) {
+            const int4 rt = s_rowtap[j0 + i];
+            float v0, v1, v2;
+            resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
+            store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
+        }
+    } else {
+        for (int i = 0; i < RPT; ++i, oi += a.LW) {
+            const int ry = ry0 + i;
+            float v0 = pad, v1 = pad, v2 = pad;
+            if (ry >= 0 && ry < a.new_h) {
+                const int4 rt = s_rowtap[j0 + i];
+                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
+            }
+            store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
+        }
     }
 }
 
@@ -466,11 +493,22 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
 // Fast-path plan: per-tile headers and (undistort) the per-tile pre-resolved remap table.  Returns false when the
 // geometry is not eligible (the generic kernel below takes over).
 static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                         const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,
                          const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy,
-                         std::vector<int4>& hdr, std::vector<unsigned>& lut, int& pitch_u, int& rows_u, size_t& raw_words) {
+                         std::vector<int4>& hdr, std::vector<unsigned>& lut, int& pitch_u, int& rows_u, size_t& raw_words,
+                         int& lut_stride) {
     const vti_geometry& g = h->g;
     const int fw = h->p.frame_w, fh = h->p.frame_h;
     if (fw & 3) return false;
+    if (h->resize_mode == 1) {
+        // no-saturation guarantee of resize_px, and the unconditional read of column sx + 1
+        for (int d = 0; d < g.new_w; ++d) {
+            if (xa[2 * d] < 0 || xa[2 * d + 1] < 0 || xa[2 * d] + xa[2 * d + 1] > 2049) return false;
+            if (xi[d] + 1 > fw - 1 && xa[2 * d + 1] != 0) return false;
+        }
+        for (int d = 0; d < g.new_h; ++d)
+            if (yb[2 * d] < 0 || yb[2 * d + 1] < 0 || yb[2 * d] + yb[2 * d + 1] > 2049) return false;
+    }
     const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
     hdr.assign((size_t)ntx * nty * 2, make_int4(0, 0, 0, 0));
     pitch_u = 4; rows_u = 1; raw_words = 0;
@@ -497,9 +535,10 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
             pitch_u = std::max(pitch_u, (ncols + 3) & ~3);
             hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
         }
+    lut_stride = (rows_u * pitch_u + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
     if (!und_ix) return true;
-    // pass 2: raw boxes + remap entries
-    lut.assign((size_t)ntx * nty * rows_u * pitch_u, 0u);
+    // pass 2: raw boxes + remap entries (entry 0 = offset 0, weights 0: a valid cell for the padded tail)
+    lut.assign((size_t)ntx * nty * lut_stride, 0u);
     for (size_t t = 0; t < (size_t)ntx * nty; ++t) {
         const int4 f = hdr[2 * t + 1];
         const int r_lo = f.x, c_lo = f.y, nrows = f.z;
@@ -521,7 +560,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
         if ((size_t)bw * bh > 16384) return false;                  // 16-bit byte offsets
         raw_words = std::max(raw_words, (size_t)bw * bh);
         hdr[2 * t] = make_int4(bx0, by0, bw, bh);
-        unsigned* L = lut.data() + t * rows_u * pitch_u;
+        unsigned* L = lut.data() + t * lut_stride;
         for (int r = 0; r < nrows; ++r)
             for (int c = 0; c < pitch_u; ++c) {
                 const int sy = r_lo + r, sx = c_lo + c;
@@ -540,6 +579,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
 }
 
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,
                 const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy) {
     const vti_geometry& g = h->g;
     const int fw = h->p.frame_w, fh = h->p.frame_h;
@@ -547,22 +587,26 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
     {
         std::vector<int4> hdr;
         std::vector<unsigned> lut;
-        int pitch_u = 0, rows_u = 0;
+        int pitch_u = 0, rows_u = 0, lut_stride = 0;
         size_t raw_words = 0;
-        if (k1_fast_plan(h, xi, yi, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words)) {
-            const size_t smem = ((size_t)rows_u * pitch_u + raw_words) * 4;
+        if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride)) {
+            const int und_words = (rows_u * pitch_u + 4 + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
+            const size_t smem = ((size_t)und_words + raw_words) * 4;
             if (smem <= 100 * 1024) {
                 h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
                 h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;
+                h->k1_und_words = und_words; h->k1_lut_stride = lut_stride;
                 VTI_CUDA(cudaMalloc((void**)&h->d_k1_tiles, sizeof(int4) * hdr.size()));
                 VTI_CUDA(cudaMemcpy(h->d_k1_tiles, hdr.data(), sizeof(int4) * hdr.size(), cudaMemcpyHostToDevice));
                 if (und_ix) {
                     VTI_CUDA(cudaMalloc((void**)&h->d_k1_lut, sizeof(unsigned) * lut.size()));
                     VTI_CUDA(cudaMemcpy(h->d_k1_lut, lut.data(), sizeof(unsigned) * lut.size(), cudaMemcpyHostToDevice));
-                    VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                } else {
-                    VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 }
+                const int sm = (int)smem;
+                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
                 return VTI_OK;
             }
         }
@@ -652,11 +696,15 @@ int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cu
         f.tap_x_idx = h->d_tap_x_idx; f.tap_x_a = h->d_tap_x_a; f.tap_y_i = h->d_tap_y_i; f.tap_y_b = h->d_tap_y_b;
         f.h = h->p.frame_h; f.w = h->p.frame_w; f.new_h = h->g.new_h; f.new_w = h->g.new_w;
         f.top = h->g.top; f.left = h->g.left; f.LH = h->g.LH; f.LW = h->g.LW;
-        f.area2x = (h->resize_mode == 2); f.flip = h->p.channel_flip;
+        f.flip = h->p.channel_flip;
         f.pitch_u = h->k1_pitch_u; f.rows_u = h->k1_rows_u;
+        f.und_words = h->k1_und_words; f.lut_stride = h->k1_lut_stride;
         dim3 grid((f.LW + TX - 1) / TX, (f.LH + TY - 1) / TY, B);
-        if (h->k1_mode == MODE_FAST_REMAP) k1_fast_kernel<true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
-        else k1_fast_kernel<false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        const bool remap = h->k1_mode == MODE_FAST_REMAP, area = h->resize_mode == 2;
+        if (remap && area) k1_fast_kernel<true, true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        else if (remap) k1_fast_kernel<true, false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        else if (area) k1_fast_kernel<false, true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        else k1_fast_kernel<false, false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
         h->launches++;
         VTI_CUDA(cudaGetLastError());
         return VTI_OK;

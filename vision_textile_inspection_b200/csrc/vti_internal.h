@@ -41,6 +41,7 @@ struct vti_handle {
     int resize_mode;                               // 1 bilinear (incl. identity taps), 2 exact-2x area
     int k1_mode, k1_pitch_u, k1_rows_u;            // staging mode + shared footprint buffer shape (k1 plan)
     size_t k1_smem;
+    int k1_und_words, k1_lut_stride;               // fast path: footprint buffer words, table entries per tile
     int4* d_k1_tiles;                              // per-tile headers (fast path) / raw bounding boxes (MODE_RAW)
     unsigned* d_k1_lut;                            // per-tile pre-resolved remap entries (fast path, undistort)
     // ---- measurement tables (device)
@@ -77,6 +78,7 @@ void vti_set_error(const std::string& s);
 
 // kernel launchers (each returns VTI_OK / VTI_ECUDA)
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
+                const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,
                 const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy);
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s);
 int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* p5, int B, cudaStream_t s);
