@@ -307,32 +307,53 @@ struct K1FastArgs {
     int lut_stride;             // entries per tile (multiple of FT_CHUNK)
 };
 
-// Stage rows [y0, y0+nr) x 4-pixel groups [x0, x0 + 4*ng) of the frame as packed words; anything outside the image
-// becomes 0 (the zero margin of cv2.remap's BORDER_CONSTANT).  x0 % 4 == 0 and w % 4 == 0.
+// Stage rows [y0, y0+nr) x 8-pixel groups [x0, x0 + 8*ng) of the frame as packed words (B | G<<8 | R<<16, byte 3 = 0);
+// anything outside the image becomes 0 (the zero margin of cv2.remap's BORDER_CONSTANT).  x0 % 8 == 0, w % 8 == 0, so a
+// group is 24 contiguous 8-byte-aligned bytes and never straddles the image edge.  Loads of STAGE_R rounds are issued
+// back to back from clamped addresses (no branch between them) so that 3*STAGE_R 64-bit loads are in flight per
+// thread; v3.1 waited on one group at a time and spent 40 % of its stall samples here.
+constexpr int STAGE_R = 3;
 __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
                                           unsigned* dst, int tid, int flip) {
     const int total = ng * nr;
     const float inv_ng = 1.0f / (float)ng;
-#pragma unroll 2
-    for (int i = tid; i < total; i += FT_THREADS) {
-        // i / ng for i < 2^14, ng <= 2^8: (i + 0.5) / ng is never within 1/(2 ng) of an integer, far above fp32 error
-        const int r = (int)(((float)i + 0.5f) * inv_ng);
-        const int g = i - r * ng;
-        const int y = y0 + r, x = x0 + 4 * g;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if ((unsigned)y < (unsigned)h && (unsigned)x < (unsigned)w) {
-            const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(frame + ((size_t)y * w + x) * 3);
-            const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-            v.x = w0 & 0xFFFFFFu;
-            v.y = __funnelshift_r(w0, w1, 24) & 0xFFFFFFu;
-            v.z = __funnelshift_r(w1, w2, 16) & 0xFFFFFFu;
-            v.w = w2 >> 8;
-            if (flip) {
-                v.x = __byte_perm(v.x, 0, 0x3012); v.y = __byte_perm(v.y, 0, 0x3012);
-                v.z = __byte_perm(v.z, 0, 0x3012); v.w = __byte_perm(v.w, 0, 0x3012);
-            }
+    // PRMT selectors: byte 4 (of the zero second operand) clears the top byte; the flipped variants reverse B and R
+    const unsigned sel_lo = flip ? 0x4012u : 0x4210u;      // word already holds the pixel in bytes 0..2
+    const unsigned sel_hi = flip ? 0x4123u : 0x4321u;      // pixel in bytes 1..3
+    for (int base = tid; base < total; base += STAGE_R * FT_THREADS) {
+        uint2 q[STAGE_R][3];
+        bool ok[STAGE_R];
+#pragma unroll
+        for (int k = 0; k < STAGE_R; ++k) {
+            const int i = base + k * FT_THREADS;
+            // i / ng for i < 2^14, ng <= 2^7: (i + 0.5) / ng is never within 1/(2 ng) of an integer, far above fp32 error
+            const int r = (int)(((float)i + 0.5f) * inv_ng);
+            const int g = i - r * ng;
+            const int y = y0 + r, x = x0 + 8 * g;
+            ok[k] = (i < total) && ((unsigned)y < (unsigned)h) && ((unsigned)x < (unsigned)w);
+            const unsigned off = ok[k] ? (unsigned)(y * w + x) * 3u : 0u;        // frames are < 2^31 bytes
+            const uint2* __restrict__ src = reinterpret_cast<const uint2*>(frame + off);
+            q[k][0] = __ldg(src); q[k][1] = __ldg(src + 1); q[k][2] = __ldg(src + 2);
         }
-        *reinterpret_cast<uint4*>(dst + 4 * i) = v;
+#pragma unroll
+        for (int k = 0; k < STAGE_R; ++k) {
+            const int i = base + k * FT_THREADS;
+            if (i >= total) break;
+            uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+            if (ok[k]) {
+                const unsigned w0 = q[k][0].x, w1 = q[k][0].y, w2 = q[k][1].x, w3 = q[k][1].y, w4 = q[k][2].x, w5 = q[k][2].y;
+                lo.x = __byte_perm(w0, 0u, sel_lo);
+                lo.y = __byte_perm(__funnelshift_r(w0, w1, 24), 0u, sel_lo);
+                lo.z = __byte_perm(__funnelshift_r(w1, w2, 16), 0u, sel_lo);
+                lo.w = __byte_perm(w2, 0u, sel_hi);
+                hi.x = __byte_perm(w3, 0u, sel_lo);
+                hi.y = __byte_perm(__funnelshift_r(w3, w4, 24), 0u, sel_lo);
+                hi.z = __byte_perm(__funnelshift_r(w4, w5, 16), 0u, sel_lo);
+                hi.w = __byte_perm(w5, 0u, sel_hi);
+            }
+            uint4* d = reinterpret_cast<uint4*>(dst + 8 * i);
+            d[0] = lo; d[1] = hi;
+        }
     }
 }
 
@@ -420,21 +441,23 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
     // ------------------------------------------------------------------------------------------- stage (+ remap)
     if (nrows > 0) {
         if (!REMAP) {
-            stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 2, nrows, s_und, tid, a.flip);
+            stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 3, nrows, s_und, tid, a.flip);
         } else {
             unsigned* s_raw = s_dyn + a.und_words;
-            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 2, h0.w, s_raw, tid, a.flip);
+            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, tid, a.flip);
             __syncthreads();
             const unsigned char* raw = reinterpret_cast<const unsigned char*>(s_raw);
             const unsigned bw4 = (unsigned)h0.z * 4u;
             const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
             unsigned* dst = s_und + tid;
             const int n_it = (nrows * a.pitch_u + FT_CHUNK - 1) / FT_CHUNK;     // table and buffer are padded
-#pragma unroll 2
-            for (int it = 0; it < n_it; ++it, lut += FT_CHUNK, dst += FT_CHUNK) {
-                const unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
+            unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
+            for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
+                lut += FT_CHUNK;                               // next entries in flight while these are computed
+                const unsigned n0 = __ldg(lut), n1 = __ldg(lut + FT_THREADS);   // (the table has one spare chunk)
                 dst[0] = remap_fast(raw, e0, bw4);
                 dst[FT_THREADS] = remap_fast(raw, e1, bw4);
+                e0 = n0; e1 = n1;
             }
         }
     }
@@ -499,7 +522,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                          int& lut_stride) {
     const vti_geometry& g = h->g;
     const int fw = h->p.frame_w, fh = h->p.frame_h;
-    if (fw & 3) return false;
+    if (fw & 7) return false;
     if (h->resize_mode == 1) {
         // no-saturation guarantee of resize_px, and the unconditional read of column sx + 1
         for (int d = 0; d < g.new_w; ++d) {
@@ -511,7 +534,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
     }
     const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
     hdr.assign((size_t)ntx * nty * 2, make_int4(0, 0, 0, 0));
-    pitch_u = 4; rows_u = 1; raw_words = 0;
+    pitch_u = 8; rows_u = 1; raw_words = 0;
     // pass 1: footprints
     for (int ty = 0; ty < nty; ++ty)
         for (int tx = 0; tx < ntx; ++tx) {
@@ -528,17 +551,17 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                 c_lo = std::min(c_lo, xi[rx]);
                 c_hi = std::max(c_hi, std::min(xi[rx] + 1, fw - 1));
             }
-            c_lo &= ~3;
+            c_lo &= ~7;
             const int nrows = r_hi - r_lo + 1, ncols = c_hi - c_lo + 1;
-            if (nrows > MAXROWS || ncols > MAXCOLS + 4) return false;
+            if (nrows > MAXROWS || ncols > MAXCOLS + 8) return false;
             rows_u = std::max(rows_u, nrows);
-            pitch_u = std::max(pitch_u, (ncols + 3) & ~3);
+            pitch_u = std::max(pitch_u, (ncols + 7) & ~7);
             hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
         }
     lut_stride = (rows_u * pitch_u + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
     if (!und_ix) return true;
     // pass 2: raw boxes + remap entries (entry 0 = offset 0, weights 0: a valid cell for the padded tail)
-    lut.assign((size_t)ntx * nty * lut_stride, 0u);
+    lut.assign((size_t)ntx * nty * lut_stride + FT_CHUNK, 0u);      // + one spare chunk: the loop prefetches
     for (size_t t = 0; t < (size_t)ntx * nty; ++t) {
         const int4 f = hdr[2 * t + 1];
         const int r_lo = f.x, c_lo = f.y, nrows = f.z;
@@ -554,8 +577,8 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                 minx = std::min(minx, x); maxx = std::max(maxx, x);
                 miny = std::min(miny, y); maxy = std::max(maxy, y);
             }
-        const int bx0 = (minx >= 0) ? (minx & ~3) : -4;
-        const int bx1 = (maxx + 2 + 3) & ~3;                        // exclusive, covers x + 1
+        const int bx0 = (minx >= 0) ? (minx & ~7) : -8;
+        const int bx1 = (maxx + 2 + 7) & ~7;                        // exclusive, covers x + 1
         const int bw = bx1 - bx0, by0 = miny, bh = maxy + 2 - miny;
         if ((size_t)bw * bh > 16384) return false;                  // 16-bit byte offsets
         raw_words = std::max(raw_words, (size_t)bw * bh);
