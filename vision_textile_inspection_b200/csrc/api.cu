@@ -170,7 +170,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
-                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut};
+                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -263,13 +263,15 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     const size_t B = p->max_batch;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
-    alloc((void**)&h->d_cand_count, sizeof(int32_t) * B);
+    alloc((void**)&h->d_cand_count, sizeof(int32_t) * (B + 1));
     alloc((void**)&h->d_cand_key, sizeof(unsigned long long) * B * vti_k3_cap_pad(g.max_candidates));
     alloc((void**)&h->d_cand_box, sizeof(float4) * B * g.A);
     alloc((void**)&h->d_det_coef, sizeof(float) * B * p->max_det * VTI_NM);
     alloc((void**)&h->d_env, sizeof(int32_t) * B * g.LW);
     alloc((void**)&h->d_env_frame, sizeof(int32_t) * B * fw);
     alloc((void**)&h->d_flags, sizeof(int32_t) * B);
+    h->units_per_det = ((g.ph + 1 + VTI_K4_UR - 1) / VTI_K4_UR) * ((g.pw + 1 + VTI_K4_UC - 1) / VTI_K4_UC);
+    alloc((void**)&h->d_units, sizeof(uint2) * B * p->max_det * h->units_per_det);
     if (e != cudaSuccess) {
         vti_set_error(std::string("vti_create: cudaMalloc: ") + cudaGetErrorString(e));
         vti_destroy(h);
@@ -346,7 +348,7 @@ extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, 
     mark(h, 2, s);
     if ((rc = vti_launch_k2(h, p3, p4, p5, B, s))) return rc;
     mark(h, 3, s);
-    if ((rc = vti_launch_k3(h, coef, B, dets, counts, s))) return rc;
+    if ((rc = vti_launch_k3(h, coef, B, dets, counts, masks != nullptr, s))) return rc;
     mark(h, 4, s);
     rc = vti_launch_k4(h, proto, B, dets, counts, masks, s);
     mark(h, 5, s);
@@ -412,7 +414,7 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     VTI_CUDA(cudaMemcpyAsync(h->d_coef, coef, sizeof(float) * nb * VTI_NM * g.A, cudaMemcpyHostToDevice, s));
     VTI_CUDA(cudaMemcpyAsync(h->d_proto, proto, sizeof(float) * nb * VTI_NM * g.ph * g.pw, cudaMemcpyHostToDevice, s));
     if ((rc = vti_launch_k2(h, h->d_p[0], h->d_p[1], h->d_p[2], B, s))) return rc;
-    if ((rc = vti_launch_k3(h, h->d_coef, B, h->d_dets, h->d_counts, s))) return rc;
+    if ((rc = vti_launch_k3(h, h->d_coef, B, h->d_dets, h->d_counts, 0, s))) return rc;
     if ((rc = vti_launch_k4(h, h->d_proto, B, h->d_dets, h->d_counts, nullptr, s))) return rc;
     if ((rc = vti_launch_k5(h, B, h->d_dets, h->d_counts, h->d_results, s))) return rc;
     if (net_in)

@@ -121,7 +121,7 @@ int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* 
     a.cand_count = h->d_cand_count;
     a.cand_key = h->d_cand_key;
     a.cand_box = h->d_cand_box;
-    VTI_CUDA(cudaMemsetAsync(h->d_cand_count, 0, sizeof(int32_t) * B, s));
+    VTI_CUDA(cudaMemsetAsync(h->d_cand_count, 0, sizeof(int32_t) * (h->p.max_batch + 1), s));   // + K4 unit counter
     k2_decode_kernel<<<dim3(nblk, B), K2_THREADS, 0, s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());

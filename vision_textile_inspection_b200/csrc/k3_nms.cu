@@ -42,6 +42,9 @@ struct K3Args {
     int roi_active, rx1, ry1, rx2, ry2;
     int stitch_id, fabric_id;
     int env_init;
+    int ph, pw, all_dets, units_per_det;
+    int32_t* unit_count;        // one counter for the whole batch
+    uint2* units;
 };
 
 __device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4 b, float barea, double thr) {
@@ -64,6 +67,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     __shared__ int s_sup[CHUNK];
     __shared__ unsigned long long s_row[CHUNK];
     __shared__ int s_nk;
+    __shared__ int s_upre[MAX_DET_CAP + 1];     // exclusive prefix of K4 work units per kept detection
+    __shared__ int s_ubase;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int n = a.cand_count[b];
@@ -192,6 +197,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
 
     // ---- 3. epilogue
     vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
+    int4* s_win = reinterpret_cast<int4*>(s_kbox);        // the sweep is over: s_kbox is reused for the crop windows
+    int nu = 0;                                            // K4 work units of this thread's detection
+    __syncthreads();
     if (tid < nk) {
         const unsigned long long key = keys[s_kidx[tid]];
         const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
@@ -225,6 +233,52 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         d.cx = qnan; d.cy = qnan; d.left_px = qnan; d.right_px = qnan;
         d.width_mm = qnan; d.edge_y = qnan; d.dist_mm = qnan; d.reserved = 0.0;
         dets[tid] = d;
+        const bool wanted = a.all_dets || ((f & VTI_F_IN_ROI) && (f & (VTI_F_STITCH | VTI_F_FABRIC)));
+        const VtiWindow w = vti_det_window(d.box_lb, a.ph, a.pw);
+        s_win[tid] = make_int4(w.cx_lo, w.cx_hi, w.cy_lo, w.cy_hi);
+        if (wanted && !w.empty)
+            nu = ((w.cy_hi - w.cy_lo + 2 + VTI_K4_UR - 1) / VTI_K4_UR) * ((w.cx_hi - w.cx_lo + 2 + VTI_K4_UC - 1) / VTI_K4_UC);
+    }
+    // ---- K4 work units: one per (kept detection, VTI_K4_UR x VTI_K4_UC block of interpolation cells)
+    {
+        // block-wide exclusive scan (1024 threads = 32 warps)
+        int incl = nu;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __shared__ int s_wsum[32];
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int ws = s_wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += v;
+            }
+            s_wsum[lane] = ws;
+        }
+        __syncthreads();
+        const int excl = incl - nu + (warp ? s_wsum[warp - 1] : 0);
+        if (tid <= nk) s_upre[tid] = excl;                 // s_upre[nk] = total (nu = 0 there)
+        const int total = s_wsum[31];
+        if (tid == 0) s_ubase = total ? atomicAdd(a.unit_count, total) : 0;
+        __syncthreads();
+        uint2* __restrict__ units = a.units + s_ubase;
+        for (int i = tid; i < total; i += K3_THREADS) {
+            int lo = 0, hi = nk - 1;                       // last detection with s_upre[k] <= i
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_upre[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            const int k = lo, local = i - s_upre[k];
+            const int4 w = s_win[k];
+            const int nb = (w.y - w.x + 2 + VTI_K4_UC - 1) / VTI_K4_UC;
+            const int br = local / nb, bc = local - br * nb;
+            units[i] = make_uint2((unsigned)b | ((unsigned)k << 16), (unsigned)br | ((unsigned)bc << 16));
+        }
     }
     // coefficient gather: [32][A] strided -> compact [nk][32]
     const float* __restrict__ coef = a.coef + (size_t)b * VTI_NM * a.A;
@@ -257,7 +311,7 @@ int vti_k3_prepare(int cap) {
     return VTI_OK;
 }
 
-int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, cudaStream_t s) {
+int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, int all_dets, cudaStream_t s) {
     K3Args a;
     a.cand_count = h->d_cand_count;
     a.cand_key = h->d_cand_key;
@@ -289,6 +343,9 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
     }
     a.stitch_id = h->p.stitch_id; a.fabric_id = h->p.fabric_id;
     a.env_init = (h->p.variant == 1) ? INT_MAX : -1;
+    a.ph = h->g.ph; a.pw = h->g.pw; a.all_dets = all_dets; a.units_per_det = h->units_per_det;
+    a.unit_count = h->d_cand_count + h->p.max_batch;
+    a.units = h->d_units;
     k3_nms_kernel<<<B, K3_THREADS, vti_k3_smem_bytes(h->g.max_candidates), s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());

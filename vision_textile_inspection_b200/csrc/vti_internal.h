@@ -13,6 +13,8 @@ static_assert(sizeof(vti_det) == 160, "vti_det must stay 160 bytes");
 #define VTI_CAND_CAP_MAX 16384
 #define VTI_K1_TX 128        // K1 output tile
 #define VTI_K1_TY 16
+#define VTI_K4_UR 6          // K4 work unit: interpolation cells per unit, rows x cols
+#define VTI_K4_UC 16
 
 // Per-axis letterbox-pixel -> frame-pixel multiplicity tables of cv2.resize(INTER_NEAREST) (measurement.py:78-79).
 // A letterbox row Y is hit by cnt[Y] frame rows whose indices sum to sum[Y]; first/last are the extreme frame rows.
@@ -48,13 +50,15 @@ struct vti_handle {
     AxisLut lutY, lutX;                            // [LH], [LW]
     int32_t* d_xmap;                               // [frame_w] frame col -> letterbox col
     // ---- post scratch (device), sized for max_batch
-    int32_t* d_cand_count;                         // [B]
+    int32_t* d_cand_count;                         // [max_batch + 1]; the last entry counts K4 work units
     unsigned long long* d_cand_key;                // [B][cap]
     float4* d_cand_box;                            // [B][A]   xyxy by anchor
     float* d_det_coef;                             // [B][max_det][32]
     int32_t* d_env;                                // [B][LW]  envelope in frame rows at letterbox columns
     int32_t* d_env_frame;                          // [B][frame_w]
     int32_t* d_flags;                              // [B] overflow etc.
+    uint2* d_units;                                // K4 work units (frame | det << 16, block row | block col << 16)
+    int units_per_det;                             // capacity per detection slot
     // ---- host-buffer path
     cudaStream_t own_stream;
     uint8_t* d_frames; float* d_net_in; float* d_p[3]; float* d_coef; float* d_proto;
@@ -82,12 +86,30 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
                 const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy);
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s);
 int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* p5, int B, cudaStream_t s);
-int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, cudaStream_t s);
+int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, int all_dets, cudaStream_t s);
 int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const int32_t* counts, uint32_t* masks,
                   cudaStream_t s);
 int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* res, cudaStream_t s);
 
 #ifdef __CUDACC__
+// Where a detection's mask can be non-zero.  crop_mask keeps prototype pixel (Y, X) iff X >= x1/4 && X < x2/4 &&
+// Y >= y1/4 && Y < y2/4 (float compares on integer grid coordinates); the bilinear upsample spreads a kept pixel over
+// the interpolation cells around it.  Cell (R, C) = the 4x4 output pixels between prototype rows R-1, R and columns
+// C-1, C (rows 4R-2 .. 4R+1): the non-zero cells of a detection are R in [cy_lo, cy_hi+1], C in [cx_lo, cx_hi+1].
+struct VtiWindow {
+    int cx_lo, cx_hi, cy_lo, cy_hi;   // cropped prototype window (inclusive)
+    bool empty;
+};
+__device__ __forceinline__ VtiWindow vti_det_window(const float* box, int ph, int pw) {
+    const float dx1 = box[0] * 0.25f, dy1 = box[1] * 0.25f, dx2 = box[2] * 0.25f, dy2 = box[3] * 0.25f;
+    VtiWindow w;
+    w.cx_lo = max((int)ceilf(dx1), 0);
+    w.cy_lo = max((int)ceilf(dy1), 0);
+    w.cx_hi = min((int)ceilf(dx2) - 1, pw - 1);
+    w.cy_hi = min((int)ceilf(dy2) - 1, ph - 1);
+    w.empty = (w.cx_lo > w.cx_hi) || (w.cy_lo > w.cy_hi) || !(dx1 == dx1) || !(dx2 == dx2) || !(dy1 == dy1) || !(dy2 == dy2);
+    return w;
+}
 // ---- bit-reproducible float32 exp / sigmoid: mirrors oracle/post_spec.py exp_spec / sigmoid_spec op for op.
 __device__ __forceinline__ float vti_exp_spec(float x) {
     x = fminf(fmaxf(x, -86.0f), 88.0f);
