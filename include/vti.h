@@ -79,6 +79,8 @@ typedef struct vti_params {
     double dist[5];               /* k1 k2 p1 p2 k3 */
     double R[9];                  /* Rodrigues(rvec), row major */
     double t[3];                  /* tvec, metres */
+    double iou_threshold;         /* predict(iou=...) as the DOUBLE torchvision.ops.nms compares against
+                                     (`ovr > iou_threshold`, ovr float32); 0 = use (double)iou */
 } vti_params;
 
 typedef struct vti_geometry {

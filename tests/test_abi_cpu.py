@@ -27,7 +27,7 @@ def test_exports_match_header():
 
 
 def test_struct_sizes_match_header():
-    assert C.sizeof(_lib.VtiParams) == 22 * 4 + 2 * 4 + (9 + 5 + 9 + 3) * 8
+    assert C.sizeof(_lib.VtiParams) == 22 * 4 + 2 * 4 + (9 + 5 + 9 + 3 + 1) * 8
     assert _lib.DET_DTYPE.itemsize == 160
 
 

@@ -1,0 +1,145 @@
+"""The drop-in host boundary (vision_textile_inspection_b200/app.py) against the reference's contract:
+constructor errors, the process_frame dict, error paths, and -- on the GPU -- the VERBATIM reference's frame sequence
+(tests/golden/scenes.json, written by oracle/gen_golden.py through /root/reference/measurement.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from vision_textile_inspection_b200 import app as A
+from vision_textile_inspection_b200 import synth
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def write_calibration(tmp_path, extr="extrinsics"):
+    c = helpers.load_calib()
+    cp, ep = tmp_path / "camera_calibration.json", tmp_path / "extrinsics.json"
+    cp.write_text(json.dumps({"camera_matrix": c["camera_matrix"], "dist_coeffs": c["dist_coeffs"]}))
+    ep.write_text(json.dumps(c[extr]))
+    return str(cp), str(ep)
+
+
+def test_constructor_raises_like_the_reference(tmp_path):
+    cp, ep = write_calibration(tmp_path)
+    with pytest.raises(FileNotFoundError, match="Calibration file missing"):
+        A.StitchMeasurementApp(str(tmp_path / "nope.json"), ep, "best_Model.pt", camera_index=None)
+    with pytest.raises(FileNotFoundError, match="Extrinsics file missing"):
+        A.StitchMeasurementApp(cp, str(tmp_path / "nope.json"), "best_Model.pt", camera_index=None)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(tmp_path):
+    from vision_textile_inspection_b200 import _lib
+    cp, ep = write_calibration(tmp_path)
+    with pytest.raises(_lib.VtiError):
+        A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, backbone=lambda x: None)
+
+
+def test_reference_defaults_are_mirrored():
+    assert (A.CONF_THRESH, A.IOU_THRESH, A.MAX_DETECTIONS) == (0.20, 0.25, 200)          # config.py:71-73
+    assert (A.FRAME_BUFFER, A.MIN_STITCHES, A.MAX_PX_DISTANCE, A.ENVELOPE_NEIGHBORHOOD) == (8, 3, 250, 3)
+    assert A.ROI_DEFAULT == (1, 10, 1270, 300, 760)                                       # config.py:91-95
+
+
+class PlantedBackbone:
+    """Stands in for the PyTorch YOLOv8-seg backbone: returns the planted raw head tensors of the queued seeds."""
+
+    def __init__(self, cfg):
+        self.cfg, self.queue = cfg, []
+
+    def __call__(self, net_in):
+        B = net_in.shape[0]
+        heads = [synth.planted_head(self.cfg, self.queue.pop(0)) for _ in range(B)]
+        dev = net_in.device
+        lv = [torch.from_numpy(np.stack([h["levels"][l] for h in heads])).to(dev) for l in range(3)]
+        return (*lv, torch.from_numpy(np.stack([h["coef"] for h in heads])).to(dev),
+                torch.from_numpy(np.stack([h["proto"] for h in heads])).to(dev))
+
+
+@pytest.mark.gpu
+def test_process_frame_reproduces_the_verbatim_reference_sequence(tmp_path):
+    seq = json.load(open(os.path.join(G, "scenes.json")))["sequence"]
+    cfg = synth.CONFIGS[seq["config"]]
+    cp, ep = write_calibration(tmp_path)
+    bb = PlantedBackbone(cfg)
+    app = A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, calib_w=cfg.frame_w, calib_h=cfg.frame_h,
+                                 backbone=bb, roi=cfg.roi(), imgsz=cfg.imgsz)
+    assert app.cap is None and np.allclose(app.n_c, [0.2283871182499797, 0.7296665720553019, 0.6445355054940998])
+    for fr in seq["frames"]:
+        bb.queue.append(fr["seed"])
+        frame = synth.fabric_frame(cfg, fr["seed"])
+        before = frame.copy()
+        annotated, m = app.process_frame(frame)
+        assert np.array_equal(frame, before) and annotated is not frame and annotated.shape == frame.shape
+        assert set(m) >= {"edge_distance_mm", "stitch_width_mm", "stitch_count", "timestamp"}
+        assert m["stitch_count"] == fr["stitch_count"]
+        assert m.get("error") == fr.get("error"), m
+        for key in ("edge_distance_mm", "stitch_width_mm"):
+            if fr[key] is None:
+                assert m[key] is None, (key, m)
+            else:
+                assert m[key] is not None and abs(m[key] - fr[key]) <= 1e-3 * fr[key], (key, m, fr)    # bar: 0.1 %
+    assert list(app.frame_buf_dist) == pytest.approx(seq["frames"][-1]["buf_dist"], rel=1e-3)
+
+
+@pytest.mark.gpu
+def test_process_frame_error_paths_never_raise(tmp_path):
+    cfg = synth.CONFIGS["native"]
+    cp, ep = write_calibration(tmp_path)
+
+    def broken(net_in):
+        raise RuntimeError("backbone exploded")
+    app = A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, backbone=broken, roi=cfg.roi())
+    frame = synth.fabric_frame(cfg, 3)
+    annotated, m = app.process_frame(frame)
+    assert m["error"] == "Model inference failed" and m["edge_distance_mm"] is None and m["stitch_count"] == 0
+    assert np.array_equal(annotated, frame)
+
+    def empty(net_in):                                       # no detections at all -> 'Fabric not detected'
+        B, dev = net_in.shape[0], net_in.device
+        lv = [torch.full((B, 64 + cfg.nc, cfg.LH // s, cfg.LW // s), -20.0, device=dev) for s in (8, 16, 32)]
+        return (*lv, torch.zeros((B, 32, cfg.anchors), device=dev),
+                torch.zeros((B, 32, cfg.LH // 4, cfg.LW // 4), device=dev))
+    app2 = A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, backbone=empty, roi=cfg.roi())
+    _, m2 = app2.process_frame(frame)
+    assert m2["error"] == "Fabric not detected" and m2["stitch_count"] == 0
+
+
+@pytest.mark.gpu
+def test_predict_inner_boundary_matches_oracle():
+    """B200Predictor.predict(rgb, conf=, iou=, max_det=, imgsz=) -> r.boxes.cls / r.boxes.xyxy / r.masks.data."""
+    from oracle import cv_fixed, ultra_ref
+    cfg = synth.CONFIGS["native"]
+    calib = helpers.load_calib()
+    K = cv_fixed.scale_K(np.array(calib["camera_matrix"]), cfg.frame_w, cfg.frame_h)
+    bb = PlantedBackbone(cfg)
+    seen = {}
+
+    def spy(net_in):
+        seen["net_in"] = net_in.clone()
+        return bb(net_in)
+    pred = A.B200Predictor(spy, K, calib["dist_coeffs"])
+    seed = 1
+    bb.queue.append(seed)
+    bgr = synth.fabric_frame(cfg, seed)
+    rgb = bgr[..., ::-1].copy()                               # measurement.py:205 hands predict() an RGB array
+    r = pred.predict(rgb, verbose=False, conf=cfg.conf, iou=cfg.iou, max_det=cfg.max_det, imgsz=cfg.imgsz)[0]
+    # the network input equals Ultralytics' letterbox of the RGB array with its channel flip
+    ref_in = ultra_ref.preprocess([rgb], cfg.imgsz, flip_channels=True).numpy()
+    assert np.array_equal(seen["net_in"].cpu().numpy(), ref_in)
+    hd = synth.planted_head(cfg, seed)
+    ref = ultra_ref.postprocess([l[None] for l in hd["levels"]], hd["coef"][None], hd["proto"][None],
+                                (cfg.frame_h, cfg.frame_w), cfg.conf, cfg.iou, cfg.max_det, cfg.nc)[0]
+    assert np.array_equal(r.boxes.cls.numpy(), ref.boxes.cls.numpy())
+    assert np.abs(r.boxes.xyxy.numpy() - ref.boxes.xyxy.numpy()).max() <= 1e-3
+    got, exp = r.masks.data.numpy() > 0, ref.masks.data.numpy() > 0
+    assert got.shape == exp.shape
+    for k in range(got.shape[0]):
+        if exp[k].sum() >= 1000:
+            assert np.logical_and(got[k], exp[k]).sum() / np.logical_or(got[k], exp[k]).sum() >= 0.999
+        else:
+            assert np.logical_xor(got[k], exp[k]).sum() <= 1

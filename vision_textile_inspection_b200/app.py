@@ -1,0 +1,305 @@
+"""Drop-in host side of the reference's detect-and-measure call, above the C ABI.
+
+Two boundaries are mirrored, same names / argument meaning / error behaviour as the reference:
+
+  outer   StitchMeasurementApp(calib_path, extr_path, model_path, camera_index=0, calib_w=640, calib_h=640,
+                               frame_buffer=8, min_stitches=3, stitch_id=0, fabric_id=1)
+          .process_frame(frame) -> (annotated, measurements)          /root/reference/measurement.py:123-126, 188-511
+          (constructed at /root/reference/main.py:80-91, called at main.py:211); force_camera_resolution(cap, w, h)
+          is importable from here as well (main.py:16, 198).
+  inner   B200Predictor.predict(rgb, verbose=False, conf=, iou=, max_det=, imgsz=) -> [Results]
+          with r.boxes.cls / r.boxes.xyxy / r.masks.data                /root/reference/measurement.py:208-210, 244-245, 74-75
+          Assigning a B200Predictor to the reference app's `.model` accelerates pre + post with zero edits there.
+
+The YOLOv8-seg backbone stays in PyTorch and only produces the raw head tensors: a `backbone` is any callable
+`net_in (B,3,LH,LW) float32 cuda -> (p3, p4, p5, coef, proto)` (see include/vti.h for the layouts).  Everything around
+it -- letterbox, decode, NMS, masks, measurement -- runs in libvti.so on the GPU; there is no CPU fallback.
+The only host arithmetic kept here is what the reference keeps as frame-ordered state: the two 8-deep median deques
+(measurement.py:149-150, 474-484).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from collections import deque
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import EngineConfig, InspectionEngine
+
+# /root/reference/config.py:59-95 defaults (the reference star-imports them; here they are constructor keywords)
+CALIB_W, CALIB_H = 1280, 960
+CONF_THRESH, IOU_THRESH, MAX_DETECTIONS = 0.20, 0.25, 200
+FRAME_BUFFER, MIN_STITCHES = 8, 3
+MAX_PX_DISTANCE, ENVELOPE_NEIGHBORHOOD = 250, 3
+STITCH_CLASS_ID, FABRIC_CLASS_ID = 0, 1
+ROI_DEFAULT = (1, 10, CALIB_W - 10, 300, CALIB_H - 200)      # enabled, x_min, x_max, y_min, y_max
+ROI_BORDER_COLOR, ROI_BORDER_THICKNESS = (144, 238, 144), 2
+CAMERA_AUTO_EXPOSURE, CAMERA_EXPOSURE = 1, 150
+
+_ERRORS = {_lib.ST_NO_FABRIC: "Fabric not detected", _lib.ST_NO_STITCH: "No stitches detected"}
+
+
+def load_json(path):
+    with open(path, "r") as f:
+        return json.load(f)
+
+
+def force_camera_resolution(cap, w, h):
+    """Same contract as /root/reference/measurement.py:23-42: set the capture size, report what the camera gave."""
+    import cv2
+    cap.set(cv2.CAP_PROP_FRAME_WIDTH, w)
+    cap.set(cv2.CAP_PROP_FRAME_HEIGHT, h)
+    time.sleep(2)
+    aw, ah = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    cap.set(cv2.CAP_PROP_AUTO_EXPOSURE, CAMERA_AUTO_EXPOSURE)
+    cap.set(cv2.CAP_PROP_EXPOSURE, CAMERA_EXPOSURE)
+    if aw != w or ah != h:
+        print(f"Warning: camera resolution {aw}x{ah}, expected {w}x{h}")
+    return aw, ah
+
+
+def backbone_from_ultralytics(model_path: str, device="cuda"):
+    """Wrap an Ultralytics YOLOv8-seg checkpoint so that it returns RAW head tensors (no decode, no NMS).
+
+    Needs the `ultralytics` package and the weight file, neither of which exists in the build container
+    (/root/reference/.MISSING_LARGE_BLOBS): this adapter is provided for integration and is NOT covered by tests.
+    """
+    try:
+        from ultralytics import YOLO
+    except Exception as e:  # pragma: no cover
+        raise RuntimeError("ultralytics is not installed: pass backbone=<callable> instead") from e
+    net = YOLO(model_path).model.to(device).eval()  # pragma: no cover
+    head = net.model[-1]                            # pragma: no cover
+
+    @torch.no_grad()
+    def run(net_in):                                # pragma: no cover
+        head.training, head.export = True, False     # training-mode forward = raw per-level maps, coefficients, protos
+        try:
+            out = net(net_in)
+        finally:
+            head.training = False
+        feats, coef, proto = out[0], out[1], out[2]
+        return feats[0].contiguous(), feats[1].contiguous(), feats[2].contiguous(), coef.contiguous(), proto.contiguous()
+    return run
+
+
+class _Boxes:
+    def __init__(self, cls, xyxy, conf):
+        self.cls, self.xyxy, self.conf = cls, xyxy, conf
+
+
+class _Masks:
+    def __init__(self, data):
+        self.data = data
+
+
+class Results:
+    """The slice of ultralytics' Results that measurement.py reads (:242-245, :74-75)."""
+
+    def __init__(self, boxes, masks, records=None, frame_result=None):
+        self.boxes, self.masks = boxes, masks
+        self.records, self.frame_result = records, frame_result
+
+
+class B200Predictor:
+    """Inner boundary: `.predict()` with the keyword arguments measurement.py:208-210 passes.
+
+    One InspectionEngine per (frame shape, imgsz, conf, iou, max_det) is created on first use and kept.
+    `channel_flip=1` reproduces BasePredictor.preprocess's `im[..., ::-1]` on the array it is handed (the reference
+    hands it RGB, so the network sees B,G,R planes -- SURVEY 8a U2).
+    """
+
+    def __init__(self, backbone, K, dist, R=None, t=None, device=None, undistort=0, nc=2, roi=(0, 0, 0, 0, 0),
+                 variant=0, channel_flip=1):
+        if not torch.cuda.is_available():
+            raise _lib.VtiError("B200Predictor needs a CUDA device: the hot path has no CPU fallback")
+        self.backbone = backbone
+        self.K, self.dist = np.asarray(K, np.float64), np.asarray(dist, np.float64).ravel()
+        self.R = np.eye(3) if R is None else np.asarray(R, np.float64)
+        self.t = np.array([0.0, 0.0, 1.0]) if t is None else np.asarray(t, np.float64)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.undistort, self.nc, self.roi, self.variant, self.channel_flip = undistort, nc, roi, variant, channel_flip
+        self.extra = {}
+        self._engines = {}
+
+    def engine_for(self, h, w, imgsz, conf, iou, max_det, batch=1) -> InspectionEngine:
+        key = (h, w, imgsz, float(conf), float(iou), int(max_det), batch)
+        eng = self._engines.get(key)
+        if eng is None:
+            ec = EngineConfig(frame_h=h, frame_w=w, K=self.K, dist=self.dist, R=self.R, t=self.t, imgsz=imgsz,
+                              nc=self.nc, conf=conf, iou=iou, max_det=max_det, max_batch=batch, variant=self.variant,
+                              undistort=self.undistort, channel_flip=self.channel_flip, roi=self.roi, **self.extra)
+            eng = self._engines[key] = InspectionEngine(ec, self.device)
+        return eng
+
+    @torch.no_grad()
+    def run(self, frames: np.ndarray, conf, iou, max_det, imgsz, export_masks=True):
+        """frames (B,h,w,3) uint8 host array -> (engine, dets, counts, results, masks) with records on the host."""
+        B, h, w = frames.shape[:3]
+        eng = self.engine_for(h, w, imgsz, conf, iou, max_det, B)
+        d_frames = torch.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
+        net_in = eng.preprocess(d_frames)                                   # K1
+        p3, p4, p5, coef, proto = self.backbone(net_in)                     # PyTorch backbone -> raw head tensors
+        dets, counts, results, masks = eng.post_measure(p3, p4, p5, coef, proto, export_masks=export_masks)  # K2..K5
+        return eng, eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results), masks
+
+    def predict(self, source, verbose=False, conf=0.25, iou=0.7, max_det=300, imgsz=640, **_ignored):
+        frames = source[None] if isinstance(source, np.ndarray) and source.ndim == 3 else np.stack(list(source))
+        eng, dets, counts, results, masks = self.run(frames, conf, iou, max_det, imgsz, export_masks=True)
+        out = []
+        for b in range(frames.shape[0]):
+            n = int(counts[b])
+            d = dets[b, :n]
+            boxes = _Boxes(torch.from_numpy(d["cls"].astype(np.float32)), torch.from_numpy(d["box_frame"].copy()),
+                           torch.from_numpy(d["conf"].copy()))
+            m = _Masks(eng.unpack_masks(masks, b, n).cpu()) if n else None
+            out.append(Results(boxes, m, d, results[b]))
+        return out
+
+
+class StitchMeasurementApp:
+    """Outer boundary: what /root/reference/main.py:80-91 constructs and main.py:211 calls.
+
+    Extra keywords (all optional) carry what the reference reads from config.py / the camera: `backbone` (callable, see
+    module docstring; default = backbone_from_ultralytics(model_path)), `roi`, `conf`, `iou`, `max_det`, `imgsz`,
+    `undistort`, `annotate`, `device`.  `camera_index=None` skips opening a camera (`.cap` is then None).
+    """
+
+    def __init__(self, calib_path, extr_path, model_path, camera_index=0, calib_w=640, calib_h=640, frame_buffer=8,
+                 min_stitches=MIN_STITCHES, stitch_id=STITCH_CLASS_ID, fabric_id=FABRIC_CLASS_ID, *, backbone=None,
+                 roi=ROI_DEFAULT, conf=CONF_THRESH, iou=IOU_THRESH, max_det=MAX_DETECTIONS, imgsz=960, undistort=0,
+                 max_px_distance=MAX_PX_DISTANCE, neighborhood=ENVELOPE_NEIGHBORHOOD, annotate=True, device=None):
+        if not os.path.exists(calib_path):
+            raise FileNotFoundError(f"Calibration file missing: {calib_path}")
+        calib = load_json(calib_path)
+        self.K = np.array(calib["camera_matrix"], dtype=np.float64)
+        self.dist = np.array(calib["dist_coeffs"], dtype=np.float64).ravel()
+        if not os.path.exists(extr_path):
+            raise FileNotFoundError(f"Extrinsics file missing: {extr_path}")
+        extr = load_json(extr_path)
+        rvec = np.array(extr["rvec"], dtype=np.float64).reshape(3, 1)
+        self.t = np.array(extr["tvec"], dtype=np.float64).reshape(3,)
+        from .engine import rodrigues
+        try:
+            import cv2
+            self.R = cv2.Rodrigues(rvec)[0]
+        except Exception:  # pragma: no cover
+            self.R = rodrigues(rvec)
+        self.n_c = self.R[:, 2].astype(np.float64)                  # measurement.py:44-48
+        self.d_c = -float(self.n_c.dot(self.t))
+
+        if backbone is None:
+            backbone = backbone_from_ultralytics(model_path)
+        self.model = B200Predictor(backbone, self.K, self.dist, self.R, self.t, device=device, undistort=undistort,
+                                   roi=tuple(int(v) for v in roi), channel_flip=0)   # frames arrive BGR: no flip
+        self.model.extra = dict(min_stitches=min_stitches, stitch_id=stitch_id, fabric_id=fabric_id,
+                                max_px_distance=max_px_distance, neighborhood=neighborhood)
+        self.conf, self.iou, self.max_det, self.imgsz = conf, iou, max_det, imgsz
+        self.annotate = annotate
+
+        self.cap, self.aw, self.ah = None, calib_w, calib_h
+        if camera_index is not None:
+            try:
+                import cv2
+                self.cap = cv2.VideoCapture(camera_index, cv2.CAP_V4L2)
+                self.aw, self.ah = force_camera_resolution(self.cap, calib_w, calib_h)
+            except Exception as e:  # pragma: no cover
+                print("Camera unavailable:", e)
+        self.frame_buf_dist = deque(maxlen=frame_buffer)
+        self.frame_buf_width = deque(maxlen=frame_buffer)
+        self.min_stitches, self.stitch_id, self.fabric_id = min_stitches, stitch_id, fabric_id
+        self.running = True
+        self.last_records = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _smooth(self, avg_dist, avg_width):
+        """measurement.py:474-484 -- frame-ordered state, hence on the host."""
+        sd = sw = None
+        if avg_dist is not None:
+            self.frame_buf_dist.append(avg_dist)
+            sd = float(np.median(self.frame_buf_dist))
+        if avg_width is not None:
+            self.frame_buf_width.append(avg_width)
+            sw = float(np.median(self.frame_buf_width))
+        return sd, sw
+
+    def _finish(self, r) -> dict:
+        status = int(r["status"]) & 0xFF
+        if status in _ERRORS:
+            return {"edge_distance_mm": None, "stitch_width_mm": None, "stitch_count": 0,
+                    "timestamp": datetime.now(), "error": _ERRORS[status]}
+        ad = None if np.isnan(r["avg_dist"]) else float(r["avg_dist"])
+        aw = None if np.isnan(r["avg_width"]) else float(r["avg_width"])
+        sd, sw = self._smooth(ad, aw)
+        return {"edge_distance_mm": sd, "stitch_width_mm": sw, "stitch_count": int(r["n_dist"]),
+                "timestamp": datetime.now()}
+
+    def process_frames(self, frames: np.ndarray):
+        """Batched form of process_frame: (B,h,w,3) uint8 -> list of measurement dicts, smoothing in frame order."""
+        eng, dets, counts, results, _ = self.model.run(frames, self.conf, self.iou, self.max_det, self.imgsz,
+                                                       export_masks=False)
+        self.last_records = [dets[b, :int(counts[b])] for b in range(frames.shape[0])]
+        return [self._finish(results[b]) for b in range(frames.shape[0])]
+
+    def process_frame(self, frame):
+        """frame: h x w x 3 uint8 BGR (not mutated).  Returns (annotated, measurements); never raises."""
+        try:
+            m = self.process_frames(np.ascontiguousarray(frame)[None])[0]
+        except Exception as e:
+            print("Model inference error:", e)
+            return frame.copy(), {"edge_distance_mm": None, "stitch_width_mm": None, "stitch_count": 0,
+                                  "timestamp": datetime.now(), "error": "Model inference failed"}
+        annotated = frame.copy()
+        if self.annotate:
+            self._draw(annotated, m)
+        return annotated, m
+
+    def _draw(self, img, m):
+        """Overlay (OUT of the hot path): ROI box, per-stitch edge lines, the info line."""
+        try:
+            import cv2
+        except Exception:  # pragma: no cover
+            return
+        h, w = img.shape[:2]
+        en, x0, x1, y0, y1 = self.model.roi
+        if en:
+            x0, x1 = max(0, min(x0, w - 1)), max(0, min(x1, w - 1))
+            y0, y1 = max(0, min(y0, h - 1)), max(0, min(y1, h - 1))
+            if x0 < x1 and y0 < y1:
+                cv2.rectangle(img, (x0, y0), (x1, y1), ROI_BORDER_COLOR, ROI_BORDER_THICKNESS)
+        rec = self.last_records[0] if self.last_records else []
+        for d in rec:
+            if d["flags"] & _lib.F_HAS_DIST:
+                cx, cy, ey = int(round(d["cx"])), int(round(d["cy"])), int(round(d["edge_y"]))
+                cv2.line(img, (cx, ey), (cx, cy), (0, 255, 0), 1)
+                cv2.circle(img, (cx, ey), 2, (255, 0, 255), -1)
+        sd, sw = m.get("edge_distance_mm"), m.get("stitch_width_mm")
+        if "error" in m:
+            text = m["error"]
+        elif sd is not None and sw is not None:
+            text = f"Edge Dist: {sd:.2f}mm | Avg Width: {sw:.2f}mm (n_d={m['stitch_count']})"
+        elif sd is not None:
+            text = f"Edge Distance: {sd:.2f}mm (n={m['stitch_count']})"
+        elif sw is not None:
+            text = f"Avg Width: {sw:.2f}mm"
+        else:
+            text = f"Insufficient stitches (need {self.min_stitches})"
+        cv2.putText(img, text, (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 0.7, (0, 0, 255), 2)
+
+    def run(self):  # pragma: no cover - camera loop of measurement.py:513-560, needs hardware
+        last = 0.0
+        while self.running and self.cap is not None:
+            ret, frame = self.cap.read()
+            if not ret:
+                continue
+            if time.time() - last >= 2.0:
+                _, m = self.process_frame(frame)
+                print(f"Edge: {m.get('edge_distance_mm', 'N/A')}mm | Width: {m.get('stitch_width_mm', 'N/A')}mm")
+                last = time.time()
+        if self.cap is not None:
+            self.cap.release()

@@ -16,6 +16,8 @@
 //   3. epilogue: un-letterbox + clip, int() truncation, ROI test on the truncated centre, class routing flags,
 //      gather of the 32 mask coefficients of each kept anchor into a compact [max_det][32] block for K4.
 #include <climits>
+#include <cmath>
+#include <cstring>
 
 #include "vti_internal.h"
 
@@ -37,7 +39,9 @@ struct K3Args {
     int32_t* env;               // [B][LW]
     int32_t* flags;             // [B] : bit0 overflow, bits 8.. = n_cand
     int cap, cap_pad, A, max_det, LW;
-    double iou;
+    double iou;                 // torchvision: (double)ovr > iou
+    double iou_mid;             // midpoint of the two float32 neighbours that straddle iou (see iou_gt)
+    int iou_tie_up;             // a quotient exactly at the midpoint rounds up (to even) -> suppressed
     float gain, padx, pady, fw, fh;
     int roi_active, rx1, ry1, rx2, ry2;
     int stitch_id, fabric_id;
@@ -47,14 +51,22 @@ struct K3Args {
     uint2* units;
 };
 
-__device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4 b, float barea, double thr) {
+// torchvision's test is `float32(inter / uni) > iou` with iou a double.  Let T be the smallest float32 above iou and
+// P its predecessor: RN(inter / uni) >= T  <=>  inter / uni > (P + T) / 2, or == with the tie rounding to T (T's
+// mantissa even).  (P + T) / 2 has 25 significant bits, uni 24: the product is exact in double, so the comparison
+// below decides exactly what the division would, without the division (it was 21 % of this kernel's instructions).
+__device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4 b, float barea, const K3Args& k) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
     const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
-    return (double)ovr > thr;
+    const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    if (uni > 0.0f && uni < 3.0e38f) {
+        const double lhs = (double)inter, rhs = __dmul_rn(k.iou_mid, (double)uni);
+        return k.iou_tie_up ? (lhs >= rhs) : (lhs > rhs);
+    }
+    return (double)__fdiv_rn(inter, uni) > k.iou;          // degenerate boxes: the literal formula (NaN -> false)
 }
 
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             const float4 cb = s_cbox[j];
             const float ca = s_carea[j];
             bool sup = false;
-            for (int k = tid >> 6; k < nk; k += K3_THREADS / CHUNK) sup |= iou_gt(s_kbox[k], s_karea[k], cb, ca, a.iou);
+            for (int k = tid >> 6; k < nk; k += K3_THREADS / CHUNK) sup |= iou_gt(s_kbox[k], s_karea[k], cb, ca, a);
             if (sup) s_sup[j] = 1;
         }
         // b. intra-chunk rows: warp w builds rows w and w+32; bit k of row j = IoU(j,k) > thr, k > j only
@@ -160,8 +172,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             const int j = warp + 32 * half;
             const float4 jb = s_cbox[j];
             const float ja = s_carea[j];
-            const bool lo = (lane > j) && iou_gt(jb, ja, s_cbox[lane], s_carea[lane], a.iou);
-            const bool hi = (lane + 32 > j) && iou_gt(jb, ja, s_cbox[lane + 32], s_carea[lane + 32], a.iou);
+            const bool lo = (lane > j) && iou_gt(jb, ja, s_cbox[lane], s_carea[lane], a);
+            const bool hi = (lane + 32 > j) && iou_gt(jb, ja, s_cbox[lane + 32], s_carea[lane + 32], a);
             const unsigned mlo = __ballot_sync(0xffffffffu, lo), mhi = __ballot_sync(0xffffffffu, hi);
             if (lane == 0) s_row[j] = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
         }
@@ -173,11 +185,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             unsigned long long removed = (unsigned long long)slo | ((unsigned long long)shi << 32);
             unsigned long long keep = 0ull;
             int room = a.max_det - nk;
-#pragma unroll 8
-            for (int i = 0; i < CHUNK; ++i) {
-                const unsigned long long row = s_row[i];
-                const bool k = (((removed >> i) & 1ull) == 0ull) && (room > 0);
-                if (k) { keep |= (1ull << i); removed |= row; --room; }
+            // jump from kept candidate to kept candidate: the chain length is the number of boxes kept in this chunk
+            // (a handful when candidates cluster around instances), not the chunk size
+            unsigned long long alive = ~removed;
+            while (alive != 0ull && room > 0) {
+                const int i = __ffsll((long long)alive) - 1;
+                keep |= (1ull << i);
+                removed |= s_row[i] | (1ull << i);
+                alive = ~removed & (i == 63 ? 0ull : (~0ull << (i + 1)));
+                --room;
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -323,7 +339,16 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
     a.env = h->d_env;
     a.flags = h->d_flags;
     a.cap = h->g.max_candidates; a.cap_pad = vti_k3_cap_pad(a.cap); a.A = h->g.A; a.max_det = h->p.max_det; a.LW = h->g.LW;
-    a.iou = (double)h->p.iou;
+    a.iou = (h->p.iou_threshold != 0.0) ? h->p.iou_threshold : (double)h->p.iou;
+    {
+        float T = (float)a.iou;                                   // smallest float32 strictly above the threshold
+        if (!((double)T > a.iou)) T = nextafterf(T, INFINITY);
+        const float P = nextafterf(T, -INFINITY);
+        a.iou_mid = ((double)P + (double)T) * 0.5;
+        unsigned bits;
+        memcpy(&bits, &T, sizeof(bits));
+        a.iou_tie_up = (bits & 1u) == 0u;
+    }
     const int fh = h->p.frame_h, fw = h->p.frame_w, LH = h->g.LH, LW = h->g.LW;
     // ops.scale_boxes: gain/pad are Python doubles, the tensor math is float32 (oracle/post_spec.py scale_boxes_spec)
     const double g1 = (double)LH / fh, g2 = (double)LW / fw;

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
     const int nwarps = gridDim.x * NWARP;
     float* sc = s_c[warp];
     const size_t plane = (size_t)a.ph * a.pw;
+    const unsigned long long plane_bytes = plane * sizeof(float);
 
     for (int u = blockIdx.x * NWARP + warp; u < total; u += nwarps) {
         const uint2 un = __ldg(a.units + u);
@@ -88,10 +89,15 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
             const int py = min(max(R0 - 1 + r, 0), a.ph - 1), px = min(max(C0 - 1 + c, 0), a.pw - 1);
             float v = 0.0f;
             if (py >= w.cy_lo && py <= w.cy_hi && px >= w.cx_lo && px <= w.cx_hi) {
-                const float* __restrict__ src = proto + (size_t)py * a.pw + px;
+                // walk the 32 channel planes with one 64-bit add per load (the compiler's own q * plane indexing costs
+                // a wide multiply + two LEAs per load)
+                const char* src = reinterpret_cast<const char*>(proto + (size_t)py * a.pw + px);
                 float pv[VTI_NM];
 #pragma unroll
-                for (int q = 0; q < VTI_NM; ++q) pv[q] = __ldg(src + q * plane);
+                for (int q = 0; q < VTI_NM; ++q) {
+                    pv[q] = __ldg(reinterpret_cast<const float*>(src));
+                    asm volatile("add.u64 %0, %0, %1;" : "+l"(src) : "l"(plane_bytes));
+                }
                 float acc = 0.0f;
 #pragma unroll
                 for (int q = 0; q < VTI_NM; q += 4) {

@@ -94,6 +94,49 @@ __device__ double np_sum(const double* a, int n) {
     return np_sum(a, n2) + np_sum(a + n2, n - n2);
 }
 
+
+// np.add.reduce on one warp, same association order as numpy's pairwise_sum: the 8 partial sums r[j] of a <= 128-element
+// block live in lanes 0..7, are combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), the tail is added sequentially, and
+// longer vectors split at n/2 rounded down to a multiple of 8.  Every lane returns the sum.  (Warp-uniform control flow.)
+__device__ double np_sum_warp(const double* a, int n, int lane) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        const int nb = n - (n % 8);
+        double r = 0.0;
+        if (lane < 8) {
+            r = a[lane];
+            for (int i = 8 + lane; i < nb; i += 8) r += a[i];
+        }
+        r += __shfl_down_sync(0xffffffffu, r, 1);
+        r += __shfl_down_sync(0xffffffffu, r, 2);
+        r += __shfl_down_sync(0xffffffffu, r, 4);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        for (int i = nb; i < n; ++i) r += a[i];
+        return r;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_sum_warp(a, n2, lane) + np_sum_warp(a + n2, n - n2, lane);
+}
+
+// dst[0..m) = src[i] for the i in [0, n) with flag[i] == want, order preserved; returns m (one warp).
+__device__ int compact_warp(const double* src, const unsigned char* flag, int want, int n, double* dst, int lane) {
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool p = (i < n) && (flag[i] == want);
+        const unsigned msk = __ballot_sync(0xffffffffu, p);
+        if (p) dst[m + __popc(msk & ((1u << lane) - 1u))] = src[i];
+        m += __popc(msk);
+    }
+    __syncwarp();
+    return m;
+}
+
 // median of the valid envelope rows at columns clip(cx_int + dx, 0, w-1), dx in [-nb, nb]; false if none valid
 __device__ __forceinline__ bool env_median(const int32_t* envf, int w, int cx_int, int nb, double* med) {
     int v[16];
@@ -243,53 +286,69 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     }
     __syncthreads();
 
-    // ---- row selection (measurement.py:390-406)
-    if (tid == 0) {
+    // ---- row selection (measurement.py:390-406): warp 0, lanes cooperate, numpy's evaluation order is kept
+    if (tid < 32) {
         int nsel = 0;
         if (ns >= 2) {
-            double c0 = s_cy[0], c1 = s_cy[0];
-            for (int i = 1; i < ns; ++i) { c0 = fmin(c0, s_cy[i]); c1 = fmax(c1, s_cy[i]); }
-            for (int i = 0; i < ns; ++i) s_lab[i] = 0;
+            double c0 = 1e300, c1 = -1e300;
+            for (int i = lane; i < ns; i += 32) { c0 = fmin(c0, s_cy[i]); c1 = fmax(c1, s_cy[i]); }
+            for (int o = 16; o > 0; o >>= 1) {
+                c0 = fmin(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+                c1 = fmax(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+            }
+            for (int i = lane; i < ns; i += 32) s_lab[i] = 0;
+            __syncwarp();
             for (int it = 0; it < 10; ++it) {
                 int ones = 0;
-                for (int i = 0; i < ns; ++i) {
-                    s_new[i] = fabs(s_cy[i] - c1) < fabs(s_cy[i] - c0);
-                    ones += s_new[i];
+                for (int base = 0; base < ns; base += 32) {
+                    const int i = base + lane;
+                    const bool nw = (i < ns) && (fabs(s_cy[i] - c1) < fabs(s_cy[i] - c0));
+                    if (i < ns) s_new[i] = nw;
+                    ones += __popc(__ballot_sync(0xffffffffu, nw));
                 }
-                if (ones == 0 || ones == ns) {
-                    if (a.variant == 1) for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
-                    break;
+                __syncwarp();
+                bool stop = (ones == 0 || ones == ns);
+                double n0 = 0.0, n1 = 0.0;
+                if (!stop) {
+                    int m = compact_warp(s_cy, s_new, 0, ns, s_tmp, lane);
+                    n0 = np_sum_warp(s_tmp, m, lane) / (double)m;
+                    __syncwarp();
+                    m = compact_warp(s_cy, s_new, 1, ns, s_tmp, lane);
+                    n1 = np_sum_warp(s_tmp, m, lane) / (double)m;
+                    __syncwarp();
+                    stop = (n0 == c0 && n1 == c1);
+                    if (stop) { n0 = c0; n1 = c1; }
                 }
-                int m = 0;
-                for (int i = 0; i < ns; ++i) if (!s_new[i]) s_tmp[m++] = s_cy[i];
-                const double n0 = np_sum(s_tmp, m) / (double)m;
-                m = 0;
-                for (int i = 0; i < ns; ++i) if (s_new[i]) s_tmp[m++] = s_cy[i];
-                const double n1 = np_sum(s_tmp, m) / (double)m;
-                if (n0 == c0 && n1 == c1) {
-                    if (a.variant == 1) for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
-                    break;
-                }
+                if (!stop || a.variant == 1)                 // the reference's break leaves the labels stale (variant 0)
+                    for (int i = lane; i < ns; i += 32) s_lab[i] = s_new[i];
+                __syncwarp();
+                if (stop) break;
                 c0 = n0; c1 = n1;
-                for (int i = 0; i < ns; ++i) s_lab[i] = s_new[i];
             }
             int chosen = 0;
             {
                 const double fm = (double)s_envsum / (double)s_envcnt;
                 double m0 = 1e9, m1 = 1e9;
-                int m = 0;
-                for (int i = 0; i < ns; ++i) if (s_lab[i] == 0) s_tmp[m++] = s_cy[i];
-                if (m > 0) m0 = np_sum(s_tmp, m) / (double)m;
-                m = 0;
-                for (int i = 0; i < ns; ++i) if (s_lab[i] == 1) s_tmp[m++] = s_cy[i];
-                if (m > 0) m1 = np_sum(s_tmp, m) / (double)m;
+                int m = compact_warp(s_cy, s_lab, 0, ns, s_tmp, lane);
+                if (m > 0) m0 = np_sum_warp(s_tmp, m, lane) / (double)m;
+                __syncwarp();
+                m = compact_warp(s_cy, s_lab, 1, ns, s_tmp, lane);
+                if (m > 0) m1 = np_sum_warp(s_tmp, m, lane) / (double)m;
+                __syncwarp();
                 chosen = (fabs(m0 - fm) < fabs(m1 - fm)) ? 0 : 1;
             }
-            for (int i = 0; i < ns; ++i) if (s_lab[i] == chosen) s_sel[nsel++] = (short)i;
+            for (int base = 0; base < ns; base += 32) {
+                const int i = base + lane;
+                const bool p = (i < ns) && (s_lab[i] == chosen);
+                const unsigned msk = __ballot_sync(0xffffffffu, p);
+                if (p) s_sel[nsel + __popc(msk & ((1u << lane) - 1u))] = (short)i;
+                nsel += __popc(msk);
+            }
         } else {
-            for (int i = 0; i < ns; ++i) s_sel[nsel++] = (short)i;
+            for (int i = lane; i < ns; i += 32) s_sel[i] = (short)i;
+            nsel = ns;
         }
-        s_nsel = nsel;
+        if (lane == 0) s_nsel = nsel;
     }
     __syncthreads();
     const int nsel = s_nsel;
@@ -308,11 +367,17 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         s_pass[j] = ok;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
         int nf = 0;
-        for (int j = 0; j < nsel; ++j) if (s_pass[j]) s_fin[nf++] = s_sel[j];
-        if (nf == 0) { for (int j = 0; j < nsel; ++j) s_fin[j] = s_sel[j]; nf = nsel; }
-        s_nfin = nf;
+        for (int base = 0; base < nsel; base += 32) {
+            const int j = base + lane;
+            const bool p = (j < nsel) && s_pass[j];
+            const unsigned msk = __ballot_sync(0xffffffffu, p);
+            if (p) s_fin[nf + __popc(msk & ((1u << lane) - 1u))] = s_sel[j];
+            nf += __popc(msk);
+        }
+        if (nf == 0) { for (int j = lane; j < nsel; j += 32) s_fin[j] = s_sel[j]; nf = nsel; }
+        if (lane == 0) s_nfin = nf;
     }
     __syncthreads();
     const int nfin = s_nfin;
@@ -353,27 +418,29 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         dets[s_st[i]].flags = f;
     }
 
-    // ---- averages (measurement.py:469-472), numpy summation order
-    if (tid == 0) {
-        int m = 0;
-        for (int j = 0; j < nfin; ++j)
-            if (s_d[j] == s_d[j]) s_tmp[m++] = s_d[j];
+    // ---- averages (measurement.py:469-472), numpy summation order, warp 0
+    __syncthreads();
+    if (tid < 32) {
+        // s_flag8 marks the valid entries so that compact_warp can gather them in order
+        for (int j = lane; j < nfin; j += 32) s_new[j] = (s_d[j] == s_d[j]);
+        __syncwarp();
+        int m = compact_warp(s_d, s_new, 1, nfin, s_tmp, lane);
         r.n_dist = m;
-        if (m >= a.min_stitches) r.avg_dist = np_sum(s_tmp, m) / (double)m;
-        m = 0;
+        if (m >= a.min_stitches) r.avg_dist = np_sum_warp(s_tmp, m, lane) / (double)m;
+        __syncwarp();
         if (a.variant == 0) {
-            for (int i = 0; i < ns; ++i)
-                if (s_w[i] == s_w[i]) s_tmp[m++] = s_w[i];
+            for (int i = lane; i < ns; i += 32) s_new[i] = (s_w[i] == s_w[i]);
+            __syncwarp();
+            m = compact_warp(s_w, s_new, 1, ns, s_tmp, lane);
         } else {
-            for (int j = 0; j < nfin; ++j) {
-                const double wv = s_w[s_fin[j]];
-                if (wv == wv) s_tmp[m++] = wv;
-            }
+            for (int j = lane; j < nfin; j += 32) { const double wv = s_w[s_fin[j]]; s_cy[j] = wv; s_new[j] = (wv == wv); }
+            __syncwarp();
+            m = compact_warp(s_cy, s_new, 1, nfin, s_tmp, lane);
         }
         r.n_width = m;
-        if (m >= a.min_stitches) r.avg_width = np_sum(s_tmp, m) / (double)m;
+        if (m >= a.min_stitches) r.avg_width = np_sum_warp(s_tmp, m, lane) / (double)m;
         r.status = VTI_ST_OK | ovf;
-        a.res[b] = r;
+        if (lane == 0) a.res[b] = r;
     }
 }
 

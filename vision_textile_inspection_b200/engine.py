@@ -91,6 +91,7 @@ class EngineConfig:
         p.min_stitches, p.max_px_distance, p.neighborhood = self.min_stitches, self.max_px_distance, self.neighborhood
         p.max_candidates = self.max_candidates
         p.conf, p.iou = self.conf, self.iou
+        p.iou_threshold = float(self.iou)          # the Python float torchvision.ops.nms receives (a C++ double)
         p.K[:] = np.asarray(self.K, np.float64).reshape(9).tolist()
         p.dist[:] = np.asarray(self.dist, np.float64).reshape(-1)[:5].tolist()
         p.R[:] = np.asarray(self.R, np.float64).reshape(9).tolist()
