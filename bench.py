@@ -187,7 +187,7 @@ def run_b200(args, cfg, rank, world, local_rank):
 
     # Pre (K1) and post+measure (K2..K5) of one batch are independent -- the backbone sits between them -- so they are
     # issued on two streams: the latency-bound per-frame CTAs of K3/K5 run under the streaming K1.
-    s_pre, s_post = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_pre, s_post = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)   # post CTAs win free SM slots
 
     def step(overlap=True):
         if not overlap:
