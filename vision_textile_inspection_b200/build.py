@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libvti.so")
+LIB = os.environ.get("VTI_LIB", os.path.join(HERE, "libvti.so"))      # (tuning sweeps build side-by-side variants)
 SOURCES = ["api.cu", "k1_preprocess.cu", "k2_decode.cu", "k3_nms.cu", "k4_masks.cu", "k5_measure.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -32,7 +32,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *COMMON, *PER_FILE.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *COMMON, *PER_FILE.get(src, []), *os.environ.get("VTI_NVCC_FLAGS", "").split(), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

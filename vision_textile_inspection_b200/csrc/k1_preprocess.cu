@@ -288,8 +288,19 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 //   * resize math: PRMT pairs the two horizontal taps of two channels, IDP.2A applies the 11-bit (a0, a1) taps;
 //     the V pass multiplies by (b0, b1), PRMT extracts both >>16 at once and IDP.2A adds them with the +2.
 // ====================================================================================================================
-constexpr int FT_THREADS = 256;
-constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration
+#ifndef VTI_FTY
+#define VTI_FTY 16
+#endif
+#ifndef VTI_FT_THREADS
+#define VTI_FT_THREADS 256
+#endif
+#ifndef VTI_FT_MINB
+#define VTI_FT_MINB 5
+#endif
+constexpr int FTX = 128, FTY = VTI_FTY;      // fast-path output tile
+constexpr int FT_THREADS = VTI_FT_THREADS;
+constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration (prefetched)
+constexpr int FT_MAXROWS = 2 * FTY + 2, FT_MAXCOLS = 2 * FTX + 2;
 
 struct K1FastArgs {
     const uint8_t* frames;
@@ -410,13 +421,13 @@ __device__ __forceinline__ void resize_px(const unsigned char* p0, const unsigne
 }
 
 template <bool REMAP, bool AREA>
-__global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a) {
+__global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const K1FastArgs a) {
     extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [und_words], then the raw box (REMAP)
     __shared__ float s_div[256];
-    __shared__ int4 s_rowtap[TY];                          // (byte offset row0, byte offset row1, b0, b1)
+    __shared__ int4 s_rowtap[FTY];                          // (byte offset row0, byte offset row1, b0, b1)
 
     const int tid = threadIdx.x;
-    const int X0 = blockIdx.x * TX, Y0 = blockIdx.y * TY;
+    const int X0 = blockIdx.x * FTX, Y0 = blockIdx.y * FTY;
     const int b = blockIdx.z;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const uint8_t* __restrict__ frame = a.frames + (size_t)b * a.h * a.w * 3;
@@ -425,8 +436,8 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
 
     const int4 h0 = __ldg(a.tile_hdr + 2 * tile), h1 = __ldg(a.tile_hdr + 2 * tile + 1);
     const int r_lo = h1.x, c_lo = h1.y, nrows = h1.z;
-    s_div[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (tid < TY) {
+    for (int i = tid; i < 256; i += FT_THREADS) s_div[i] = __fdiv_rn((float)i, 255.0f);
+    if (tid < FTY) {
         const int ry = Y0 + tid - a.top;
         int4 t = make_int4(0, 0, 0, 0);
         if (ry >= 0 && ry < a.new_h && nrows > 0) {
@@ -465,10 +476,10 @@ __global__ void __launch_bounds__(FT_THREADS) k1_fast_kernel(const K1FastArgs a)
 
     // ----------------------------------------------------------------------------------------------- resize
     const float pad = s_div[114];
-    const int X = X0 + (tid & (TX - 1));
+    const int X = X0 + (tid & (FTX - 1));
     if (X >= a.LW) return;
-    constexpr int RPT = TY / (FT_THREADS / TX);            // rows per thread
-    const int j0 = (tid / TX) * RPT;
+    constexpr int RPT = FTY / (FT_THREADS / FTX);          // rows per thread
+    const int j0 = (tid / FTX) * RPT;
     const size_t plane = (size_t)a.LH * a.LW;
     float* __restrict__ o0 = out + (size_t)(Y0 + j0) * a.LW + X;     // three plane pointers + one 32-bit row offset
     float* __restrict__ o1 = o0 + plane;
@@ -532,15 +543,15 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
         for (int d = 0; d < g.new_h; ++d)
             if (yb[2 * d] < 0 || yb[2 * d + 1] < 0 || yb[2 * d] + yb[2 * d + 1] > 2049) return false;
     }
-    const int ntx = (g.LW + TX - 1) / TX, nty = (g.LH + TY - 1) / TY;
+    const int ntx = (g.LW + FTX - 1) / FTX, nty = (g.LH + FTY - 1) / FTY;
     hdr.assign((size_t)ntx * nty * 2, make_int4(0, 0, 0, 0));
     pitch_u = 8; rows_u = 1; raw_words = 0;
     // pass 1: footprints
     for (int ty = 0; ty < nty; ++ty)
         for (int tx = 0; tx < ntx; ++tx) {
-            const int X0 = tx * TX, Y0 = ty * TY;
-            const int ry_lo = std::max(Y0 - g.top, 0), ry_hi = std::min(Y0 + TY - 1 - g.top, g.new_h - 1);
-            const int rx_lo = std::max(X0 - g.left, 0), rx_hi = std::min(X0 + TX - 1 - g.left, g.new_w - 1);
+            const int X0 = tx * FTX, Y0 = ty * FTY;
+            const int ry_lo = std::max(Y0 - g.top, 0), ry_hi = std::min(Y0 + FTY - 1 - g.top, g.new_h - 1);
+            const int rx_lo = std::max(X0 - g.left, 0), rx_hi = std::min(X0 + FTX - 1 - g.left, g.new_w - 1);
             if (ry_lo > ry_hi || rx_lo > rx_hi) continue;                     // pure padding tile: nrows = 0
             int r_lo = INT32_MAX, r_hi = -1, c_lo = INT32_MAX, c_hi = -1;
             for (int ry = ry_lo; ry <= ry_hi; ++ry) {
@@ -553,7 +564,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
             }
             c_lo &= ~7;
             const int nrows = r_hi - r_lo + 1, ncols = c_hi - c_lo + 1;
-            if (nrows > MAXROWS || ncols > MAXCOLS + 8) return false;
+            if (nrows > FT_MAXROWS || ncols > FT_MAXCOLS + 8) return false;
             rows_u = std::max(rows_u, nrows);
             pitch_u = std::max(pitch_u, (ncols + 7) & ~7);
             hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
@@ -615,7 +626,7 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
         if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride)) {
             const int und_words = (rows_u * pitch_u + 4 + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
             const size_t smem = ((size_t)und_words + raw_words) * 4;
-            if (smem <= 100 * 1024) {
+            if (smem <= 110 * 1024) {
                 h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
                 h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;
                 h->k1_und_words = und_words; h->k1_lut_stride = lut_stride;
@@ -722,7 +733,7 @@ int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cu
         f.flip = h->p.channel_flip;
         f.pitch_u = h->k1_pitch_u; f.rows_u = h->k1_rows_u;
         f.und_words = h->k1_und_words; f.lut_stride = h->k1_lut_stride;
-        dim3 grid((f.LW + TX - 1) / TX, (f.LH + TY - 1) / TY, B);
+        dim3 grid((f.LW + FTX - 1) / FTX, (f.LH + FTY - 1) / FTY, B);
         const bool remap = h->k1_mode == MODE_FAST_REMAP, area = h->resize_mode == 2;
         if (remap && area) k1_fast_kernel<true, true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
         else if (remap) k1_fast_kernel<true, false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
