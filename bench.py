@@ -63,8 +63,11 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 5.0                      # the first sample can take a second to appear
+            while not self.lines and time.time() < t_end:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -75,10 +78,10 @@ class ClockSampler:
     def stop(self, t0: float, t1: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons, power = [], None, set(), []
-        rows = [ln for (t, ln) in self.lines if t0 - 0.2 <= t <= t1 + 0.3] or [ln for (_, ln) in self.lines]
+        rows = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.1] or [ln for (_, ln) in self.lines]
         for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
@@ -226,9 +229,13 @@ def run_b200(args, cfg, rank, world, local_rank):
     for _ in range(args.steps):
         step()
     e1.record()
+    launches = eng.launch_count - l0
+    # The timed region is K steps (a few ms); nvidia-smi samples every 100 ms.  The identical loop keeps running,
+    # untimed, until >= 0.5 s of load has been sampled, so "clocks" describes this workload under load.
+    for _ in range(args.load_steps):                    # same count on every rank: step() may hold a collective
+        step()
     barrier()
     t_wall1 = time.time()
-    launches = eng.launch_count - l0
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -307,7 +314,8 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "net_in": [cfg.LW, cfg.LH], "anchors": cfg.anchors, "undistort": cfg.undistort,
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                   "unique_frames": n_unique, "streams": "K1 || K2-K5 (two streams)",
+                   "unique_frames": n_unique, "streams": "K1 || K2-K5 (two streams, post at high priority)",
+                   "clock_sampling": "nvidia-smi every 100 ms over the timed steps + an untimed continuation of the same loop",
                    "status_ok_frames": int((res["status"] == 0).sum())},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -339,6 +347,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
