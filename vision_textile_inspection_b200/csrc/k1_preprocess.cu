@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 //     the V pass multiplies by (b0, b1), PRMT extracts both >>16 at once and IDP.2A adds them with the +2.
 // ====================================================================================================================
 #ifndef VTI_FTY
-#define VTI_FTY 16
+#define VTI_FTY 32
 #endif
 #ifndef VTI_FT_THREADS
 #define VTI_FT_THREADS 256
@@ -297,7 +297,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 #ifndef VTI_FT_MINB
 #define VTI_FT_MINB 5
 #endif
-constexpr int FTX = 128, FTY = VTI_FTY;      // fast-path output tile
+#ifndef VTI_FTX
+#define VTI_FTX 64
+#endif
+constexpr int FTX = VTI_FTX, FTY = VTI_FTY;  // fast-path output tile
 constexpr int FT_THREADS = VTI_FT_THREADS;
 constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration (prefetched)
 constexpr int FT_MAXROWS = 2 * FTY + 2, FT_MAXCOLS = 2 * FTX + 2;

@@ -60,6 +60,7 @@ template <bool EXPORT>
 __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a) {
     __shared__ float s_c[NWARP][(UR + 1) * SCW];
     __shared__ __align__(16) float s_coef[NWARP][VTI_NM];   // registers go to the 32 in-flight prototype loads
+    __shared__ int s_envw[NWARP][4 * UC];                   // fabric envelope of the unit's columns (one RED each)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int total = *a.unit_count;
     const int nwarps = gridDim.x * NWARP;
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
         const float inv_ncw = 1.0f / (float)ncw;
         __syncwarp();
         s_coef[warp][lane] = __ldg(a.det_coef + ((size_t)b * a.max_det + k) * VTI_NM + lane);
+        if (fabric) { s_envw[warp][lane] = a.upper ? INT_MAX : -1; s_envw[warp][lane + 32] = a.upper ? INT_MAX : -1; }
+        const int ex0 = 4 * C0 - 2;                        // first output column of the unit
         const float* __restrict__ proto = a.proto + (size_t)b * VTI_NM * plane;
         __syncwarp();
         // (1) logits -> sigmoid -> crop over the corner rectangle (replicate-clamped at the plane border)
@@ -136,10 +139,10 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
                     cmin = min(cmin, a.lx.next_first[xa]); cmax = max(cmax, a.lx.prev_last[xb]);
                     if (fabric) {
                         const int f_env = a.upper ? a.ly.next_first[ya] : a.ly.prev_last[yb];
-                        int32_t* __restrict__ env = a.env + (size_t)b * a.LW;
                         for (int X = xa; X <= xb; ++X)
                             if (a.lx.cnt[X] > 0) {
-                                if (a.upper) atomicMin(env + X, f_env); else atomicMax(env + X, f_env);
+                                if (a.upper) atomicMin(&s_envw[warp][X - ex0], f_env);
+                                else atomicMax(&s_envw[warp][X - ex0], f_env);
                             }
                     }
                 }
@@ -170,9 +173,8 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
                                 cmin = min(cmin, a.lx.first[X]);
                                 cmax = max(cmax, a.lx.last[X]);
                                 if (fabric) {
-                                    int32_t* __restrict__ env = a.env + (size_t)b * a.LW;
-                                    if (a.upper) atomicMin(env + X, a.ly.first[Y]);
-                                    else atomicMax(env + X, a.ly.last[Y]);
+                                    if (a.upper) atomicMin(&s_envw[warp][X - ex0], a.ly.first[Y]);
+                                    else atomicMax(&s_envw[warp][X - ex0], a.ly.last[Y]);
                                 }
                             }
                         }
@@ -183,6 +185,16 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
                         if ((unsigned)(rowbits >> 32)) atomicOr(wp + 1, (unsigned)(rowbits >> 32));
                     }
                 }
+            }
+        }
+        if (fabric) {                                       // one RED per touched column and unit
+            __syncwarp();
+            int32_t* __restrict__ env = a.env + (size_t)b * a.LW;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int ev = s_envw[warp][lane + 32 * hh], X = ex0 + lane + 32 * hh;
+                if (a.upper) { if (ev != INT_MAX) atomicMin(env + X, ev); }
+                else { if (ev >= 0) atomicMax(env + X, ev); }
             }
         }
         // (3) warp reduction, one set of global atomics per unit
