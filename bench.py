@@ -104,6 +104,10 @@ def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 1):
     import cv2
     import torch
     from oracle import cv_fixed, measure_port, ultra_ref
+    ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:          # torchrun exports OMP_NUM_THREADS=1: the CPU arm gets every host thread
+        torch.set_num_threads(ncpu)
+    cv2.setNumThreads(ncpu)
     K = cv_fixed.scale_K(np.array(calib["camera_matrix"]), cfg.frame_w, cfg.frame_h)
     dist = np.array(calib["dist_coeffs"])
     ex = calib[cfg.extrinsics]
@@ -184,7 +188,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     d_lv = [l.to(dev) for l in host_lv]
     d_coef, d_proto = host["coef"].to(dev), host["proto"].to(dev)
     net_in = torch.empty((B, 3, eng.LH, eng.LW), dtype=torch.float32, device=dev)
-    outs = eng.alloc_outputs(B)
+    packed, outs = shard.alloc_packed(B, cfg.max_det, dev)            # records + results + counts in one buffer: one gather
     in_bytes = (d_frames.numel() + 4 * (sum(l.numel() for l in d_lv) + d_coef.numel() + d_proto.numel()))
     out_bytes = 4 * net_in.numel()
 
@@ -200,12 +204,12 @@ def run_b200(args, cfg, rank, world, local_rank):
             eng.preprocess(d_frames, out=net_in)
             dets, counts, results, _ = eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=outs)
             if world > 1:
-                shard.gather_records(dets, counts, results)
+                shard.gather_packed(packed)
             return
         with torch.cuda.stream(s_post):
             dets, counts, results, _ = eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=outs)
             if world > 1:
-                shard.gather_records(dets, counts, results)
+                shard.gather_packed(packed)
         with torch.cuda.stream(s_pre):
             eng.preprocess(d_frames, out=net_in)
 

@@ -24,3 +24,35 @@ def gather_records(dets: torch.Tensor, counts: torch.Tensor, results: torch.Tens
         dist.all_gather_into_tensor(buf, t, group=group)      # concatenated along dim 0 = global frame order
         outs.append(buf)
     return tuple(outs)
+
+
+def alloc_packed(B: int, max_det: int, device):
+    """One contiguous buffer holding a rank's records, per-frame results and counts, plus typed views into it, so
+    that the per-step exchange is ONE all-gather: (packed, (dets, counts, results, None))."""
+    from ._lib import DET_DTYPE, RESULT_DTYPE
+    nd, nr = B * max_det * DET_DTYPE.itemsize, B * RESULT_DTYPE.itemsize
+    packed = torch.zeros((nd + nr + 4 * B,), dtype=torch.uint8, device=device)
+    dets = packed[:nd].view(B, max_det, DET_DTYPE.itemsize)
+    results = packed[nd:nd + nr].view(B, RESULT_DTYPE.itemsize)
+    counts = packed[nd + nr:].view(torch.int32)
+    return packed, (dets, counts, results, None)
+
+
+def gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather of the packed per-rank buffers: (W, bytes).  Row r holds rank r's frames (global frame order = rank
+    order); unpack_packed() gives the typed views."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * packed.numel(),), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)      # flat: concatenation in rank order
+    return out.view(world, packed.numel())
+
+
+def unpack_packed(gathered: torch.Tensor, B: int, max_det: int):
+    """(W, bytes) -> dets (W*B, max_det, 160) u8, counts (W*B,) i32, results (W*B, 56) u8."""
+    from ._lib import DET_DTYPE, RESULT_DTYPE
+    W = gathered.shape[0]
+    nd, nr = B * max_det * DET_DTYPE.itemsize, B * RESULT_DTYPE.itemsize
+    dets = gathered[:, :nd].reshape(W * B, max_det, DET_DTYPE.itemsize)
+    results = gathered[:, nd:nd + nr].reshape(W * B, RESULT_DTYPE.itemsize)
+    counts = gathered[:, nd + nr:].contiguous().view(torch.int32).reshape(W * B)
+    return dets, counts, results
