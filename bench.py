@@ -174,6 +174,9 @@ def run_b200(args, cfg, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (this image's default): keep stdout = one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     calib = load_reference_calibration()
     B = cfg.batch if args.batch is None else args.batch
