@@ -291,3 +291,73 @@ def test_errors_are_reported_not_raised_into_cuda():
         eng.preprocess(torch.zeros((1, 10, 10, 3), dtype=torch.uint8, device="cuda"))
     with pytest.raises(_lib.VtiError):
         eng.preprocess(torch.zeros((2, cfg.frame_h, cfg.frame_w, 3), dtype=torch.uint8, device="cuda"))  # B > max_batch
+
+
+# ------------------------------------------------------------------------- BASELINE-size, size-independent properties
+def test_full_size_batch_properties(calib):
+    """BASELINE.json configs[1] at its full size (64 x 1280x720, undistort on) through the C ABI.  The oracle cannot
+    run 64 frames in seconds, so this checks properties: (a) batch-position invariance -- the batch holds 8 unique
+    frames repeated 8 times and every copy must give bit-identical network input, records and results; (b) the
+    first 2 frames equal the oracle exactly (K1) / to the parity bars (post + measure); (c) idempotence of a second
+    call; (d) a checksum of checksums over the whole K1 output equals 8 x the checksum of the unique part."""
+    cfg = synth.CONFIGS["cfg2"]
+    B, U = 64, 8
+    batch = synth.make_batch(cfg, B, seed0=2000, n_unique=U)
+    eng = make_engine(cfg, B)
+    d_frames = dev(batch["frames"])
+    net = eng.preprocess(d_frames)
+    args = [dev(x) for x in batch["levels"]] + [dev(batch["coef"]), dev(batch["proto"])]
+    dets, counts, results, _ = eng.post_measure(*args)
+    torch.cuda.synchronize()
+    d, c, r = eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results)
+    # (a) every repetition of a unique frame is bit-identical, wherever it sits in the batch
+    net_u = net[:U]
+    for k in range(1, B // U):
+        assert torch.equal(net[k * U:(k + 1) * U], net_u)
+        assert np.array_equal(c[k * U:(k + 1) * U], c[:U])
+        for b in range(U):
+            n = c[b]
+            assert d[k * U + b, :n].tobytes() == d[b, :n].tobytes()
+            assert r[k * U + b].tobytes() == r[b].tobytes()
+    # (d) checksum of checksums (uint32 view, wrap-around sum) over all 64 frames = 8 x the unique part
+    cs = net.view(torch.int32).to(torch.int64).sum(dim=(1, 2, 3))
+    assert int(cs.sum()) == (B // U) * int(cs[:U].sum())
+    # (b) the first frames against the oracle
+    und = (eng.cfg.K, eng.cfg.dist)
+    ref = ultra_ref.preprocess(list(batch["frames"][:2]), cfg.imgsz, undistort=und).numpy()
+    assert np.array_equal(net[:2].cpu().numpy(), ref)
+    for b in range(2):
+        sp = post_spec.postprocess_spec([l[b] for l in batch["levels"]], batch["coef"][b], cfg.conf, cfg.iou,
+                                        cfg.max_det, cfg.nc, cfg.LH, cfg.LW, cfg.frame_h, cfg.frame_w)
+        assert np.array_equal(d[b, :c[b]]["anchor"], sp["keep_anchor"])
+    assert (r["status"] == _lib.ST_OK).all()
+    # (c) idempotence: a second call on the same inputs reproduces every byte
+    dets2, counts2, results2, _ = eng.post_measure(*args)
+    net2 = eng.preprocess(d_frames)
+    torch.cuda.synchronize()
+    assert torch.equal(net2, net) and torch.equal(counts2, counts)
+    d2 = eng.dets_to_numpy(dets2)
+    for b in range(B):
+        assert d2[b, :c[b]].tobytes() == d[b, :c[b]].tobytes()
+    assert eng.results_to_numpy(results2).tobytes() == r.tobytes()
+
+
+@pytest.mark.parametrize("name,B", [("cfg3", 16), ("cfg4", 8), ("cfg5", 4)])
+def test_other_configs_batch_invariance(name, B, calib):
+    """Configs 3-5 at a reduced batch: records of a frame do not depend on its position in the batch, the stress
+    config saturates max_det, and K1 on the 4K / 1080p frames stays bit-exact against cv2."""
+    cfg = synth.CONFIGS[name]
+    batch = synth.make_batch(cfg, B, seed0=1000 * cfg.cfg_id, n_unique=2)
+    eng = make_engine(cfg, B)
+    net = eng.preprocess(dev(batch["frames"]))
+    dets, counts, results, _ = eng.post_measure(*[dev(x) for x in batch["levels"]], dev(batch["coef"]),
+                                                dev(batch["proto"]))
+    torch.cuda.synchronize()
+    d, c, r = eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results)
+    for b in range(2, B):
+        assert torch.equal(net[b], net[b % 2]) and c[b] == c[b % 2]
+        assert d[b, :c[b]].tobytes() == d[b % 2, :c[b]].tobytes() and r[b].tobytes() == r[b % 2].tobytes()
+    und = (eng.cfg.K, eng.cfg.dist) if cfg.undistort else None
+    assert np.array_equal(net[:1].cpu().numpy(), ultra_ref.preprocess(list(batch["frames"][:1]), cfg.imgsz, undistort=und).numpy())
+    if name == "cfg4":
+        assert (c == cfg.max_det).all()
