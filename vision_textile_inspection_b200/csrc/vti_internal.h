@@ -13,7 +13,7 @@ static_assert(sizeof(vti_det) == 160, "vti_det must stay 160 bytes");
 #define VTI_CAND_CAP_MAX 16384
 #define VTI_K1_TX 128        // K1 output tile
 #define VTI_K1_TY 16
-#define VTI_K4_UR 6          // K4 work unit: interpolation cells per unit, rows x cols
+#define VTI_K4_UR 4          // K4 work unit: interpolation cells per unit, rows x cols
 #define VTI_K4_UC 16
 
 // Per-axis letterbox-pixel -> frame-pixel multiplicity tables of cv2.resize(INTER_NEAREST) (measurement.py:78-79).
