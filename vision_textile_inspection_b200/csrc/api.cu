@@ -174,6 +174,9 @@ extern "C" void vti_destroy(vti_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 4; ++i)
+        if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
     for (int i = 0; i < 8; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -379,6 +382,8 @@ static int ensure_staging(vti_handle* h) {
     const vti_geometry& g = h->g;
     const size_t B = h->p.max_batch;
     VTI_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    VTI_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) VTI_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming));
     VTI_CUDA(cudaMalloc((void**)&h->d_frames, B * h->p.frame_h * h->p.frame_w * 3));
     VTI_CUDA(cudaMalloc((void**)&h->d_net_in, sizeof(float) * B * 3 * g.LH * g.LW));
     for (int l = 0; l < 3; ++l)
@@ -403,25 +408,39 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     }
     if ((rc = ensure_staging(h))) return rc;
     const vti_geometry& g = h->g;
-    cudaStream_t s = h->own_stream;
+    cudaStream_t s = h->own_stream, cs = h->copy_stream;
     const float* hp[3] = {p3, p4, p5};
-    const size_t nb = (size_t)B;
-    VTI_CUDA(cudaMemcpyAsync(h->d_frames, frames, nb * h->p.frame_h * h->p.frame_w * 3, cudaMemcpyHostToDevice, s));
-    if ((rc = vti_launch_k1(h, h->d_frames, B, h->d_net_in, s))) return rc;
-    for (int l = 0; l < 3; ++l)
-        VTI_CUDA(cudaMemcpyAsync(h->d_p[l], hp[l], sizeof(float) * nb * (64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l],
-                                 cudaMemcpyHostToDevice, s));
-    VTI_CUDA(cudaMemcpyAsync(h->d_coef, coef, sizeof(float) * nb * VTI_NM * g.A, cudaMemcpyHostToDevice, s));
-    VTI_CUDA(cudaMemcpyAsync(h->d_proto, proto, sizeof(float) * nb * VTI_NM * g.ph * g.pw, cudaMemcpyHostToDevice, s));
-    if ((rc = vti_launch_k2(h, h->d_p[0], h->d_p[1], h->d_p[2], B, s))) return rc;
-    if ((rc = vti_launch_k3(h, h->d_coef, B, h->d_dets, h->d_counts, 0, s))) return rc;
-    if ((rc = vti_launch_k4(h, h->d_proto, B, h->d_dets, h->d_counts, nullptr, s))) return rc;
-    if ((rc = vti_launch_k5(h, B, h->d_dets, h->d_counts, h->d_results, s))) return rc;
-    if (net_in)
-        VTI_CUDA(cudaMemcpyAsync(net_in, h->d_net_in, sizeof(float) * nb * 3 * g.LH * g.LW, cudaMemcpyDeviceToHost, s));
-    VTI_CUDA(cudaMemcpyAsync(dets, h->d_dets, sizeof(vti_det) * nb * h->p.max_det, cudaMemcpyDeviceToHost, s));
-    VTI_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
-    VTI_CUDA(cudaMemcpyAsync(results, h->d_results, sizeof(vti_frame_result) * nb, cudaMemcpyDeviceToHost, s));
+    // The batch goes through in up to 4 chunks: chunk i+1's host->device copies (copy stream) run under chunk i's
+    // kernels and device->host record copies (compute stream), so the call costs the PCIe time of its inputs plus
+    // one chunk of compute.
+    const int nchunk = B < 4 ? 1 : 4;
+    const size_t fsz = (size_t)h->p.frame_h * h->p.frame_w * 3, nsz = (size_t)3 * g.LH * g.LW;
+    size_t lsz[3];
+    for (int l = 0; l < 3; ++l) lsz[l] = (size_t)(64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l];
+    const size_t csz = (size_t)VTI_NM * g.A, psz = (size_t)VTI_NM * g.ph * g.pw;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk), nb = b1 - b0;
+        if (nb <= 0) continue;
+        VTI_CUDA(cudaMemcpyAsync(h->d_frames + b0 * fsz, frames + b0 * fsz, nb * fsz, cudaMemcpyHostToDevice, cs));
+        for (int l = 0; l < 3; ++l)
+            VTI_CUDA(cudaMemcpyAsync(h->d_p[l] + b0 * lsz[l], hp[l] + b0 * lsz[l], sizeof(float) * nb * lsz[l],
+                                     cudaMemcpyHostToDevice, cs));
+        VTI_CUDA(cudaMemcpyAsync(h->d_coef + b0 * csz, coef + b0 * csz, sizeof(float) * nb * csz, cudaMemcpyHostToDevice, cs));
+        VTI_CUDA(cudaMemcpyAsync(h->d_proto + b0 * psz, proto + b0 * psz, sizeof(float) * nb * psz, cudaMemcpyHostToDevice, cs));
+        VTI_CUDA(cudaEventRecord(h->chunk_ev[c], cs));
+        VTI_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
+        vti_det* cd = h->d_dets + (size_t)b0 * h->p.max_det;
+        if ((rc = vti_launch_k1(h, h->d_frames + b0 * fsz, nb, h->d_net_in + b0 * nsz, s))) return rc;
+        if ((rc = vti_launch_k2(h, h->d_p[0] + b0 * lsz[0], h->d_p[1] + b0 * lsz[1], h->d_p[2] + b0 * lsz[2], nb, s))) return rc;
+        if ((rc = vti_launch_k3(h, h->d_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
+        if ((rc = vti_launch_k4(h, h->d_proto + b0 * psz, nb, cd, h->d_counts + b0, nullptr, s))) return rc;
+        if ((rc = vti_launch_k5(h, nb, cd, h->d_counts + b0, h->d_results + b0, s))) return rc;
+        if (net_in)
+            VTI_CUDA(cudaMemcpyAsync(net_in + b0 * nsz, h->d_net_in + b0 * nsz, sizeof(float) * nb * nsz, cudaMemcpyDeviceToHost, s));
+        VTI_CUDA(cudaMemcpyAsync(dets + (size_t)b0 * h->p.max_det, cd, sizeof(vti_det) * nb * h->p.max_det, cudaMemcpyDeviceToHost, s));
+        VTI_CUDA(cudaMemcpyAsync(counts + b0, h->d_counts + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+        VTI_CUDA(cudaMemcpyAsync(results + b0, h->d_results + b0, sizeof(vti_frame_result) * nb, cudaMemcpyDeviceToHost, s));
+    }
     VTI_CUDA(cudaStreamSynchronize(s));
     return VTI_OK;
 }

@@ -60,7 +60,8 @@ struct vti_handle {
     uint2* d_units;                                // K4 work units (frame | det << 16, block row | block col << 16)
     int units_per_det;                             // capacity per detection slot
     // ---- host-buffer path
-    cudaStream_t own_stream;
+    cudaStream_t own_stream, copy_stream;
+    cudaEvent_t chunk_ev[4];
     uint8_t* d_frames; float* d_net_in; float* d_p[3]; float* d_coef; float* d_proto;
     vti_det* d_dets; int32_t* d_counts; vti_frame_result* d_results;
     size_t staged_batch;
