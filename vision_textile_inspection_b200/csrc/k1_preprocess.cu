@@ -19,6 +19,7 @@
 // HBM traffic: frame read once (tile halos hit L2) + 12*LH*LW written once; the 4 B/px remap table is L2-resident
 // across the batch.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "vti_internal.h"
@@ -565,11 +566,11 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                 c_lo = std::min(c_lo, xi[rx]);
                 c_hi = std::max(c_hi, std::min(xi[rx] + 1, fw - 1));
             }
-            c_lo &= ~7;
+            if (!und_ix) c_lo &= ~7;                               // only the direct staging needs 8-pixel groups
             const int nrows = r_hi - r_lo + 1, ncols = c_hi - c_lo + 1;
             if (nrows > FT_MAXROWS || ncols > FT_MAXCOLS + 8) return false;
             rows_u = std::max(rows_u, nrows);
-            pitch_u = std::max(pitch_u, (ncols + 7) & ~7);
+            pitch_u = std::max(pitch_u, und_ix ? ncols : ((ncols + 7) & ~7));   // remapped footprints pack tightly
             hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
         }
     lut_stride = (rows_u * pitch_u + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
@@ -628,7 +629,11 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
         size_t raw_words = 0;
         if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride)) {
             const int und_words = (rows_u * pitch_u + 4 + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
-            const size_t smem = ((size_t)und_words + raw_words) * 4;
+            size_t smem = ((size_t)und_words + raw_words) * 4;
+            // Leave room on every SM for the post kernels that run beside K1 (two streams): at most 4 resident K1 CTAs.
+            // Measured: 5 CTAs/SM make K1 alone 5 % faster and the whole pre || post step 8 % slower.
+            if (getenv("VTI_K1_SMEM_FLOOR")) smem = std::max(smem, (size_t)atoi(getenv("VTI_K1_SMEM_FLOOR")));
+            else smem = std::max(smem, (size_t)(46 * 1024 + 512));
             if (smem <= 110 * 1024) {
                 h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
                 h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;

@@ -24,6 +24,7 @@
 // Optional bit-packed mask export: cells OR their bits into the (pre-zeroed) global mask words.
 // Bound: the prototype read (128 B per prototype pixel touched); algorithmic bytes 128*ph*pw per frame.
 #include <climits>
+#include <cstdlib>
 
 #include "vti_internal.h"
 
@@ -236,7 +237,7 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
     a.LH = h->g.LH; a.LW = h->g.LW; a.ph = h->g.ph; a.pw = h->g.pw; a.max_det = h->p.max_det;
     a.upper = (h->p.variant == 1);
     // grid-stride over the device-side unit list: four 8-warp CTAs per SM
-    const int grid = 4 * h->num_sms;
+    const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : 4) * h->num_sms;
     if (masks) {
         const size_t wpm = (size_t)a.LH * (a.LW / 32);
         k4_zero_masks_kernel<<<dim3(a.max_det, B), 256, 0, s>>>(masks, counts, a.max_det, wpm);
