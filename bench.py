@@ -98,7 +98,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 1):
+def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 3, single_thread_frames: int = 0):
     """The reference CPU path on this host: cv2 undistort+letterbox, torch decode + torchvision NMS + process_mask,
     and the measure-stage port (oracle/), frame by frame like the reference (batch 1, measurement.py:208-211)."""
     import cv2
@@ -126,11 +126,28 @@ def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 1):
     nb = batch["frames"].shape[0]
     for i in range(warm):
         one(i % nb)
+    per = []
     t0 = time.perf_counter()
     for i in range(n_frames):
+        t1 = time.perf_counter()
         one(i % nb)
+        per.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
-    cores = {"os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cv2_threads": cv2.getNumThreads()}
+    cores = {"os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cv2_threads": cv2.getNumThreads(),
+             "ms_per_frame_median": 1e3 * float(np.median(per)), "ms_per_frame_p10": 1e3 * float(np.percentile(per, 10)),
+             "ms_per_frame_p90": 1e3 * float(np.percentile(per, 90))}
+    if single_thread_frames:
+        nt, nc = torch.get_num_threads(), cv2.getNumThreads()
+        torch.set_num_threads(1)
+        cv2.setNumThreads(1)
+        one(0)
+        t1 = time.perf_counter()
+        for i in range(single_thread_frames):
+            one(i % nb)
+        cores["single_thread_frames_per_s"] = single_thread_frames / (time.perf_counter() - t1)
+        cores["single_thread_sample_frames"] = single_thread_frames
+        torch.set_num_threads(nt)
+        cv2.setNumThreads(nc)
     return n_frames / dt, dt, cores
 
 
@@ -349,7 +366,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         n_cpu = args.cpu_frames
-        fps, dt, cores = cpu_reference(cfg, batch, calib, n_cpu)
+        fps, dt, cores = cpu_reference(cfg, batch, calib, n_cpu, single_thread_frames=6)
         cpu = {"value": fps, "unit": UNIT, "cores": cores["torch_threads"], "kind": "port",
                "sample": f"{n_cpu} frames of {cfg.name} in {dt:.1f}s, batch-1 loop: cv2.undistort+LetterBox, torch "
                          f"decode/torchvision nms/process_mask, measure-stage port; threads={cores}"}
