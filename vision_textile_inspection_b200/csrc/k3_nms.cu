@@ -26,7 +26,7 @@ namespace {
 constexpr int K3_THREADS = 1024;
 constexpr int CHUNK = 64;
 constexpr int MAX_DET_CAP = 1024;
-constexpr int KEYS_SMEM = 4096;     // sort buffer in shared memory; larger candidate sets sort in their global buffer
+constexpr int KEYS_SMEM = 8192;     // sort buffer in shared memory (64 KB); larger candidate sets sort in their global buffer
 
 struct K3Args {
     const int32_t* cand_count;
@@ -60,6 +60,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
     const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    // disjoint boxes (the common case: most candidates are nowhere near most kept boxes): 0 / uni > iou is false for
+    // every iou >= 0, and NaN (uni == 0) compares false as well
+    if (!(w > 0.0f && h > 0.0f) && k.iou >= 0.0) return false;
     const float inter = __fmul_rn(w, h);
     const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
     if (uni > 0.0f && uni < 3.0e38f) {
