@@ -361,3 +361,32 @@ def test_other_configs_batch_invariance(name, B, calib):
     assert np.array_equal(net[:1].cpu().numpy(), ultra_ref.preprocess(list(batch["frames"][:1]), cfg.imgsz, undistort=und).numpy())
     if name == "cfg4":
         assert (c == cfg.max_det).all()
+
+
+@pytest.mark.parametrize("n_equal", [1500, 3000])
+def test_nms_thousands_of_equal_scores(n_equal):
+    """Lazy score buckets of K3: thousands of candidates with the SAME score fall into one histogram bin -- 1500 of
+    them sort in the shared-memory buffer, 3000 overflow it and take the whole-set global sort.  Equal scores must
+    come out in ascending anchor order exactly like torchvision's stable sort, whatever the path."""
+    cfg = synth.CONFIGS["cfg4"]
+    rng = np.random.default_rng(n_equal)
+    shapes = [(cfg.LH // s, cfg.LW // s) for s in (8, 16, 32)]
+    lv = [np.full((64 + cfg.nc, hh, ww), -20.0, np.float32) for hh, ww in shapes]
+    for l in range(3):
+        lv[l][:64] = rng.normal(0, 1.5, lv[l][:64].shape).astype(np.float32)      # random DFL logits: overlapping boxes
+    flat = lv[0][64].reshape(-1)
+    flat[rng.choice(flat.size, n_equal, replace=False)] = 1.25                     # identical class-0 logits
+    lv[1][65].reshape(-1)[rng.choice(lv[1][65].size, 300, replace=False)] = rng.normal(2, 1, 300)   # plus a spread
+    coef = rng.normal(0, 1, (32, cfg.anchors)).astype(np.float32)
+    proto = rng.normal(0, 1, (32, cfg.LH // 4, cfg.LW // 4)).astype(np.float32)
+    eng = make_engine(cfg, 1)
+    dets, counts, results, _ = eng.post_measure(*[dev(x[None]) for x in lv], dev(coef[None]), dev(proto[None]))
+    torch.cuda.synchronize()
+    sp = post_spec.postprocess_spec(lv, coef, cfg.conf, cfg.iou, cfg.max_det, cfg.nc, cfg.LH, cfg.LW, cfg.frame_h,
+                                    cfg.frame_w)
+    assert sp["n_cand"] >= n_equal
+    n = int(counts[0])
+    d = eng.dets_to_numpy(dets)[0, :n]
+    assert n == len(sp["keep_anchor"]) and np.array_equal(d["anchor"], sp["keep_anchor"])
+    assert np.array_equal(d["conf"].view(np.uint32), sp["conf"].view(np.uint32))
+    assert eng.results_to_numpy(results)["n_cand"][0] == sp["n_cand"]

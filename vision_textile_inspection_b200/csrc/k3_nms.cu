@@ -26,7 +26,8 @@ namespace {
 constexpr int K3_THREADS = 1024;
 constexpr int CHUNK = 64;
 constexpr int MAX_DET_CAP = 1024;
-constexpr int KEYS_SMEM = 8192;     // sort buffer in shared memory (64 KB); larger candidate sets sort in their global buffer
+constexpr int HIST_BINS = 2048;     // score bins of the lazy bucket sort
+constexpr int KEYS_SMEM = 2048;     // sort buffer in shared memory (a score bucket holds <= 1024 keys unless one bin is oversized)
 
 struct K3Args {
     const int32_t* cand_count;
@@ -42,6 +43,8 @@ struct K3Args {
     double iou;                 // torchvision: (double)ovr > iou
     double iou_mid;             // midpoint of the two float32 neighbours that straddle iou (see iou_gt)
     int iou_tie_up;             // a quotient exactly at the midpoint rounds up (to even) -> suppressed
+    unsigned hist_lo;           // score bits of the confidence threshold (every candidate score is above it)
+    int hist_shift;             // (score bits - hist_lo) >> hist_shift < HIST_BINS for scores <= 1
     float gain, padx, pady, fw, fh;
     int roi_active, rx1, ry1, rx2, ry2;
     int stitch_id, fabric_id;
@@ -72,36 +75,17 @@ __device__ __forceinline__ bool iou_gt(const float4 a, float aarea, const float4
     return (double)__fdiv_rn(inter, uni) > k.iou;          // degenerate boxes: the literal formula (NaN -> false)
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];   // KEYS_SMEM entries
-    __shared__ float4 s_kbox[MAX_DET_CAP];      // kept boxes (class offset applied)
-    __shared__ float s_karea[MAX_DET_CAP];
-    __shared__ int s_kidx[MAX_DET_CAP];         // sorted position of each kept box
-    __shared__ float4 s_cbox[CHUNK];
-    __shared__ float s_carea[CHUNK];
-    __shared__ int s_sup[CHUNK];
-    __shared__ unsigned long long s_row[CHUNK];
-    __shared__ int s_nk;
-    __shared__ int s_upre[MAX_DET_CAP + 1];     // exclusive prefix of K4 work units per kept detection
-    __shared__ int s_ubase;
-
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int n = a.cand_count[b];
-    const bool overflow = n > a.cap;
-    n = min(n, a.cap);
-    int n_pad = 64;
-    while (n_pad < n) n_pad <<= 1;
-
-    unsigned long long* gkeys = a.cand_key + (size_t)b * a.cap_pad;
-    unsigned long long* keys = (n_pad <= KEYS_SMEM) ? s_keys : gkeys;      // generic pointer: shared or global
-    for (int i = tid; i < a.LW; i += K3_THREADS) a.env[(size_t)b * a.LW + i] = a.env_init;
-    if (tid == 0) s_nk = 0;
-
-    // ---- 1. bitonic sort, descending
-    if (n_pad <= K3_THREADS) {
+// Bitonic sort (descending) of m keys: in registers + shuffles when there is at most one key per thread, in the
+// buffer `keys` (shared or global) otherwise.  `src` is where the unsorted keys are; the result is in keys[0..m_pad).
+__device__ __forceinline__ void sort_desc(unsigned long long* keys, const unsigned long long* src, int m, int tid,
+                                          unsigned long long* s_keys) {
+    int m_pad = 64;
+    while (m_pad < m) m_pad <<= 1;
+    if (m_pad <= K3_THREADS) {
         // one key per thread in a register; partners closer than a warp come through shuffles, no barrier
-        unsigned long long key = (tid < n) ? gkeys[tid] : 0ull;
-        for (int k = 2; k <= n_pad; k <<= 1) {
+        unsigned long long key = (tid < m) ? src[tid] : 0ull;
+        __syncthreads();                                   // src may be s_keys itself
+        for (int k = 2; k <= m_pad; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 unsigned long long other;
                 if (j >= 32) {
@@ -119,14 +103,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         s_keys[tid] = key;
         __syncthreads();
     } else {
-        for (int i = tid; i < n_pad; i += K3_THREADS) {
-            if (keys == s_keys) keys[i] = (i < n) ? gkeys[i] : 0ull;
-            else if (i >= n) keys[i] = 0ull;
+        for (int i = tid; i < m_pad; i += K3_THREADS) {
+            if (keys != src) keys[i] = (i < m) ? src[i] : 0ull;
+            else if (i >= m) keys[i] = 0ull;
         }
         __syncthreads();
-        for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int k = 2; k <= m_pad; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < n_pad; i += K3_THREADS) {
+                for (int i = tid; i < m_pad; i += K3_THREADS) {
                     const int p = i ^ j;
                     if (p > i) {
                         const unsigned long long x = keys[i], y = keys[p];
@@ -138,80 +122,173 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             }
         }
     }
+}
 
-    // ---- 2. greedy sweep
+__global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];   // KEYS_SMEM entries
+    __shared__ float4 s_kbox[MAX_DET_CAP];      // kept boxes (class offset applied)
+    __shared__ float s_karea[MAX_DET_CAP];
+    __shared__ unsigned long long s_kkey[MAX_DET_CAP];   // key of each kept box
+    __shared__ float4 s_cbox[CHUNK];
+    __shared__ float s_carea[CHUNK];
+    __shared__ int s_sup[CHUNK];
+    __shared__ unsigned long long s_row[CHUNK];
+    __shared__ int s_nk, s_m, s_lo_bin;
+    __shared__ int s_upre[MAX_DET_CAP + 1];     // exclusive prefix of K4 work units per kept detection
+    __shared__ int s_ubase;
+    __shared__ int s_hist[HIST_BINS];           // candidates per score bin (lazy bucket sort)
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n = a.cand_count[b];
+    const bool overflow = n > a.cap;
+    n = min(n, a.cap);
+
+    unsigned long long* gkeys = a.cand_key + (size_t)b * a.cap_pad;
+    for (int i = tid; i < a.LW; i += K3_THREADS) a.env[(size_t)b * a.LW + i] = a.env_init;
+    if (tid == 0) s_nk = 0;
+
+    // ---- 1 + 2. sort and greedy sweep.  Up to one key per thread: one sort of everything.  More candidates (low
+    // confidence thresholds, thousands per frame): LAZY score buckets -- a histogram of the score bits cuts the
+    // candidates into descending score ranges of <= 1024 each; a range is compacted, sorted and swept only when the
+    // ranges above it left room below max_det, so the tail of low scores is usually never sorted at all.  (Equal
+    // scores share a bin, hence a bucket: the order inside a bucket is the exact (score, anchor) order.)
+    const bool bucketed = n > K3_THREADS;
+    if (bucketed) {
+        for (int i = tid; i < HIST_BINS; i += K3_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += K3_THREADS) {
+            const unsigned sb = (unsigned)(gkeys[i] >> 32);
+            atomicAdd(&s_hist[min((int)((sb - a.hist_lo) >> a.hist_shift), HIST_BINS - 1)], 1);
+        }
+    }
+    __syncthreads();
     const float4* __restrict__ gbox = a.cand_box + (size_t)b * a.A;
-    int nk = 0;
-    for (int c0 = 0; c0 < n && nk < a.max_det; c0 += CHUNK) {
-        if (tid < CHUNK) {
-            const int i = c0 + tid;
-            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-            float ar = 0.f;
-            if (i < n) {
-                const unsigned long long key = keys[i];
-                const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
-                const float off = __fmul_rn((float)(int)(key & 0xFFull), 7680.0f);
-                const float4 r = gbox[anchor];
-                bx = make_float4(__fadd_rn(r.x, off), __fadd_rn(r.y, off), __fadd_rn(r.z, off), __fadd_rn(r.w, off));
-                ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-            }
-            s_cbox[tid] = bx;
-            s_carea[tid] = ar;
-            s_sup[tid] = (i < n) ? 0 : 1;
-        }
-        __syncthreads();
-        // a. against every box kept in earlier chunks
-        {
-            const int j = tid & (CHUNK - 1);
-            const float4 cb = s_cbox[j];
-            const float ca = s_carea[j];
-            bool sup = false;
-            for (int k = tid >> 6; k < nk; k += K3_THREADS / CHUNK) sup |= iou_gt(s_kbox[k], s_karea[k], cb, ca, a);
-            if (sup) s_sup[j] = 1;
-        }
-        // b. intra-chunk rows: warp w builds rows w and w+32; bit k of row j = IoU(j,k) > thr, k > j only
+    int nk = 0, hi_bin = HIST_BINS - 1;
+    bool last = !bucketed;
+    for (;;) {
+        int m = n;
+        unsigned long long* keys = s_keys;
+        if (!bucketed) {
+            sort_desc(s_keys, gkeys, n, tid, s_keys);
+        } else {
+            // next bucket: bins [lo_bin, hi_bin] holding <= K3_THREADS candidates (at least one bin)
+            if (warp == 0) {
+                int acc = 0, top = hi_bin, taken = 0;
+                bool stop = false;
+                while (!stop && top >= 0) {
+                    const int bin = top - lane;
+                    int c = bin >= 0 ? s_hist[bin] : 0, pre = c;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int j = warp + 32 * half;
-            const float4 jb = s_cbox[j];
-            const float ja = s_carea[j];
-            const bool lo = (lane > j) && iou_gt(jb, ja, s_cbox[lane], s_carea[lane], a);
-            const bool hi = (lane + 32 > j) && iou_gt(jb, ja, s_cbox[lane + 32], s_carea[lane + 32], a);
-            const unsigned mlo = __ballot_sync(0xffffffffu, lo), mhi = __ballot_sync(0xffffffffu, hi);
-            if (lane == 0) s_row[j] = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
-        }
-        __syncthreads();
-        // c. sequential resolve on one warp (all lanes redundantly; the row loads do not depend on the chain)
-        if (warp == 0) {
-            const unsigned slo = __ballot_sync(0xffffffffu, s_sup[lane] != 0);
-            const unsigned shi = __ballot_sync(0xffffffffu, s_sup[lane + 32] != 0);
-            unsigned long long removed = (unsigned long long)slo | ((unsigned long long)shi << 32);
-            unsigned long long keep = 0ull;
-            int room = a.max_det - nk;
-            // jump from kept candidate to kept candidate: the chain length is the number of boxes kept in this chunk
-            // (a handful when candidates cluster around instances), not the chunk size
-            unsigned long long alive = ~removed;
-            while (alive != 0ull && room > 0) {
-                const int i = __ffsll((long long)alive) - 1;
-                keep |= (1ull << i);
-                removed |= s_row[i] | (1ull << i);
-                alive = ~removed & (i == 63 ? 0ull : (~0ull << (i + 1)));
-                --room;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                        if (lane >= o) pre += v;
+                    }
+                    const unsigned fit = __ballot_sync(0xffffffffu, bin >= 0 && acc + pre <= K3_THREADS);
+                    int cnt = (fit == 0xffffffffu) ? 32 : (__ffs(~fit) - 1);   // leading lanes (bins) that still fit
+                    if (cnt == 0 && taken == 0) cnt = 1;                       // a single oversized bin still forms a bucket
+                    const int got = __shfl_sync(0xffffffffu, pre, max(cnt, 1) - 1);
+                    if (cnt > 0) { acc += got; taken += cnt; top -= cnt; }
+                    stop = cnt < 32;
+                }
+                if (lane == 0) { s_lo_bin = top + 1; s_m = 0; }
             }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int i = lane + 32 * half;
-                if ((keep >> i) & 1ull) {
-                    const int pos = nk + __popcll(keep & ((1ull << i) - 1ull));
-                    s_kbox[pos] = s_cbox[i];
-                    s_karea[pos] = s_carea[i];
-                    s_kidx[pos] = c0 + i;
+            __syncthreads();
+            const int lo_bin = s_lo_bin;
+            for (int i = tid; i < n; i += K3_THREADS) {
+                const unsigned long long key = gkeys[i];
+                const int bin = min((int)(((unsigned)(key >> 32) - a.hist_lo) >> a.hist_shift), HIST_BINS - 1);
+                if (bin >= lo_bin && bin <= hi_bin) {
+                    const int pos = atomicAdd(&s_m, 1);
+                    if (pos < KEYS_SMEM) s_keys[pos] = key;
                 }
             }
-            if (lane == 0) s_nk = nk + __popcll(keep);
+            __syncthreads();
+            m = s_m;
+            last = lo_bin <= 0;
+            hi_bin = lo_bin - 1;
+            if (m > KEYS_SMEM) {
+                // a pathological score distribution (thousands of candidates in one bin): sort everything at once in
+                // the global buffer and start over
+                m = n; keys = gkeys; nk = 0; last = true;
+                __syncthreads();
+                if (tid == 0) s_nk = 0;
+            }
+            if (m > 0) sort_desc(keys, keys, m, tid, s_keys);
+            __syncthreads();
         }
-        __syncthreads();
-        nk = s_nk;
+        // ---- greedy sweep over this bucket's sorted keys, 64 at a time
+        for (int c0 = 0; c0 < m && nk < a.max_det; c0 += CHUNK) {
+            if (tid < CHUNK) {
+                const int i = c0 + tid;
+                float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+                float ar = 0.f;
+                if (i < m) {
+                    const unsigned long long key = keys[i];
+                    const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
+                    const float off = __fmul_rn((float)(int)(key & 0xFFull), 7680.0f);
+                    const float4 r = gbox[anchor];
+                    bx = make_float4(__fadd_rn(r.x, off), __fadd_rn(r.y, off), __fadd_rn(r.z, off), __fadd_rn(r.w, off));
+                    ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+                }
+                s_cbox[tid] = bx;
+                s_carea[tid] = ar;
+                s_sup[tid] = (i < m) ? 0 : 1;
+            }
+            __syncthreads();
+            // a. against every box kept so far
+            {
+                const int j = tid & (CHUNK - 1);
+                const float4 cb = s_cbox[j];
+                const float ca = s_carea[j];
+                bool sup = false;
+                for (int k = tid >> 6; k < nk; k += K3_THREADS / CHUNK) sup |= iou_gt(s_kbox[k], s_karea[k], cb, ca, a);
+                if (sup) s_sup[j] = 1;
+            }
+            // b. intra-chunk rows: warp w builds rows w and w+32; bit k of row j = IoU(j,k) > thr, k > j only
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int j = warp + 32 * half;
+                const float4 jb = s_cbox[j];
+                const float ja = s_carea[j];
+                const bool lo = (lane > j) && iou_gt(jb, ja, s_cbox[lane], s_carea[lane], a);
+                const bool hi = (lane + 32 > j) && iou_gt(jb, ja, s_cbox[lane + 32], s_carea[lane + 32], a);
+                const unsigned mlo = __ballot_sync(0xffffffffu, lo), mhi = __ballot_sync(0xffffffffu, hi);
+                if (lane == 0) s_row[j] = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+            }
+            __syncthreads();
+            // c. sequential resolve on one warp (all lanes redundantly; the row loads do not depend on the chain)
+            if (warp == 0) {
+                const unsigned slo = __ballot_sync(0xffffffffu, s_sup[lane] != 0);
+                const unsigned shi = __ballot_sync(0xffffffffu, s_sup[lane + 32] != 0);
+                unsigned long long removed = (unsigned long long)slo | ((unsigned long long)shi << 32);
+                unsigned long long keep = 0ull;
+                int room = a.max_det - nk;
+                // jump from kept candidate to kept candidate: the chain length is the number of boxes kept in this
+                // chunk (a handful when candidates cluster around instances), not the chunk size
+                unsigned long long alive = ~removed;
+                while (alive != 0ull && room > 0) {
+                    const int i = __ffsll((long long)alive) - 1;
+                    keep |= (1ull << i);
+                    removed |= s_row[i] | (1ull << i);
+                    alive = ~removed & (i == 63 ? 0ull : (~0ull << (i + 1)));
+                    --room;
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int i = lane + 32 * half;
+                    if ((keep >> i) & 1ull) {
+                        const int pos = nk + __popcll(keep & ((1ull << i) - 1ull));
+                        s_kbox[pos] = s_cbox[i];
+                        s_karea[pos] = s_carea[i];
+                        s_kkey[pos] = keys[c0 + i];
+                    }
+                }
+                if (lane == 0) s_nk = nk + __popcll(keep);
+            }
+            __syncthreads();
+            nk = s_nk;
+        }
+        if (last || nk >= a.max_det) break;
     }
 
     // ---- 3. epilogue
@@ -220,7 +297,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     int nu = 0;                                            // K4 work units of this thread's detection
     __syncthreads();
     if (tid < nk) {
-        const unsigned long long key = keys[s_kidx[tid]];
+        const unsigned long long key = s_kkey[tid];
         const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
         const int cls = (int)(key & 0xFFull);
         const float4 r = gbox[anchor];
@@ -304,7 +381,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     float* __restrict__ dc = a.det_coef + (size_t)b * a.max_det * VTI_NM;
     for (int i = tid; i < nk * VTI_NM; i += K3_THREADS) {
         const int k = i >> 5, c = i & 31;
-        const unsigned long long key = keys[s_kidx[k]];
+        const unsigned long long key = s_kkey[k];
         const int anchor = 0xFFFFFF - (int)((key >> 8) & 0xFFFFFFull);
         dc[i] = __ldg(coef + (size_t)c * a.A + anchor);
     }
@@ -370,6 +447,14 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
         }
     }
     a.stitch_id = h->p.stitch_id; a.fabric_id = h->p.fabric_id;
+    {
+        const float c = h->p.conf > 0.0f ? h->p.conf : 0.0f, one = 1.0f;
+        unsigned cb, ob;
+        memcpy(&cb, &c, 4); memcpy(&ob, &one, 4);
+        a.hist_lo = cb;
+        a.hist_shift = 0;
+        while (((ob - cb) >> a.hist_shift) >= (unsigned)HIST_BINS) ++a.hist_shift;
+    }
     a.env_init = (h->p.variant == 1) ? INT_MAX : -1;
     a.ph = h->g.ph; a.pw = h->g.pw; a.all_dets = all_dets; a.units_per_det = h->units_per_det;
     a.unit_count = h->d_cand_count + h->p.max_batch;
