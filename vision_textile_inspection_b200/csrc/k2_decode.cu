@@ -207,7 +207,7 @@ int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* 
     a.cand_box = h->d_cand_box;
     VTI_CUDA(cudaMemsetAsync(h->d_cand_count, 0, sizeof(int32_t) * (h->p.max_batch + 1), s));   // + K4 unit counter
     k2_decode_kernel<<<dim3(nblk, B), K2_THREADS, 0, s>>>(a);
-    k2_box_kernel<<<dim3(8, B), K2_THREADS, 0, s>>>(a);       // 8 x 256 lanes = 512 candidates per pass and frame
+    k2_box_kernel<<<dim3(16, B), K2_THREADS, 0, s>>>(a);      // 16 x 256 lanes = 1024 candidates per pass and frame; idle blocks exit
     h->launches += 2;
     VTI_CUDA(cudaGetLastError());
     return VTI_OK;

@@ -6,12 +6,14 @@
 // Spec: oracle/post_spec.py nms_spec / scale_boxes_spec (bit-identical: same fp32 op order, no FMA, IoU compared
 // against the threshold in double exactly like the C++ kernel's `ovr > iou_threshold`).
 //
-//   1. bitonic sort of the 64-bit keys (score bits | ~anchor | cls) in shared memory, descending
-//      == stable descending score sort over ascending anchor order
+//   1. bitonic sort of the 64-bit keys (score bits | ~anchor | cls), descending
+//      == stable descending score sort over ascending anchor order.  Up to 1024 candidates sort in registers; more
+//      candidates are cut into descending score buckets of <= 1024 by a histogram of the score bits and each bucket
+//      is compacted + sorted only if the sweep still has room below max_det (lazy sort)
 //   2. greedy sweep in chunks of 64 sorted candidates:
 //        a. every (candidate, already-kept box) pair is tested in parallel           -> suppressed-by-earlier bits
 //        b. the 64x64 intra-chunk IoU bitmask is built with one ballot per row half  -> row masks
-//        c. one warp resolves the chunk sequentially on register bitmasks            -> keep bits
+//        c. one warp resolves the chunk, jumping kept-to-kept with ffs on register bitmasks -> keep bits
 //      stops as soon as max_det boxes are kept ( == torchvision nms followed by [:max_det] )
 //   3. epilogue: un-letterbox + clip, int() truncation, ROI test on the truncated centre, class routing flags,
 //      gather of the 32 mask coefficients of each kept anchor into a compact [max_det][32] block for K4.
