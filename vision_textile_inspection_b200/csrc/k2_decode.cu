@@ -6,11 +6,15 @@
 // Spec: oracle/post_spec.py decode_spec / candidates_spec -- every float op below is the same single-rounded
 // IEEE op in the same order (no FMA contraction), so boxes and scores are bit-identical to the spec.
 //
-// Phase 1: one thread per anchor; a warp covers 32 consecutive anchors of one level so the class-logit reads are
-// coalesced 128-byte lines; candidates go to a block-local list.  Phase 2: one lane per (candidate, box side) -- the
-// 16-bin softmax expectations of a block's candidates run on full warps instead of on the 1-3 candidate lanes of a
-// divergent warp (v1: 43 us -> v2).  Candidates are appended with one atomicAdd per block; the order inside the list is irrelevant because K3 sorts by the composite
-// key (score bits, ~anchor) which reproduces torchvision's stable descending sort over ascending anchor order.
+// Two kernels:
+//   k2_decode_kernel  4 anchors per thread (a warp covers 32 consecutive anchors of one level: coalesced 128-byte
+//                     class-logit lines, all of a thread's loads in flight at once), class sigmoid + `> conf`, one
+//                     atomicAdd per block to append the (score bits | ~anchor | class) keys.  The order inside the
+//                     list is irrelevant: K3 sorts by the composite key, which reproduces torchvision's stable
+//                     descending sort over ascending anchor order.
+//   k2_box_kernel     DFL softmax expectation of the CANDIDATES only, over the flat per-frame lists: one lane per
+//                     (candidate, box side), the four sides meet through shuffles.  (Fused into the classifying
+//                     kernel, the block that owned a row of stitches decoded ~400 candidates alone.)
 #include "vti_internal.h"
 
 int vti_k3_cap_pad(int cap);
