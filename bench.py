@@ -344,6 +344,21 @@ def run_b200(args, cfg, rank, world, local_rank):
                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                        "api": "app.B200Predictor.run: frames from pinned host memory, head tensors produced on the device"}
 
+    # ---- single-frame latency of the drop-in call path (the reference processes one frame per call, main.py:211)
+    pred1 = B200Predictor(lambda net: (d_lv[0][:1], d_lv[1][:1], d_lv[2][:1], d_coef[:1], d_proto[:1]), ecfg.K, ecfg.dist,
+                          ecfg.R, ecfg.t, device=dev, undistort=cfg.undistort, nc=cfg.nc, roi=cfg.roi(),
+                          variant=cfg.variant, channel_flip=0)
+    pred1.extra = dict(max_px_distance=ecfg.max_px_distance)
+    f1 = f_host[:1]
+    lat = []
+    for i in range(33):
+        t1 = time.perf_counter()
+        pred1.run(f1, cfg.conf, cfg.iou, cfg.max_det, cfg.imgsz, export_masks=False)
+        if i >= 3:
+            lat.append(1e3 * (time.perf_counter() - t1))
+    latency = {"ms_median": float(np.median(lat)), "ms_p90": float(np.percentile(lat, 90)), "frames": 1,
+               "api": "app.B200Predictor.run, one frame from host memory to host records (H2D + K1..K5 + D2H)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -386,6 +401,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "api": "vti_process_host (pinned host buffers, 4-chunk copy/compute pipeline)"},
         "e2e_frames_only": e2e_frames_only,
+        "latency_single_frame": latency,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * sb[names[dom]]},

@@ -390,3 +390,33 @@ def test_nms_thousands_of_equal_scores(n_equal):
     assert n == len(sp["keep_anchor"]) and np.array_equal(d["anchor"], sp["keep_anchor"])
     assert np.array_equal(d["conf"].view(np.uint32), sp["conf"].view(np.uint32))
     assert eng.results_to_numpy(results)["n_cand"][0] == sp["n_cand"]
+
+
+@pytest.mark.parametrize("nc", [3, 5])
+def test_decode_nms_other_class_counts(nc):
+    """nc != 2 (the reference model has two classes): K2's generic class loop (nc > 4) and the unrolled one (nc <= 4),
+    first-maximum tie rule and class-offset NMS stay bit-exact against the spec."""
+    import dataclasses
+    cfg = dataclasses.replace(synth.CONFIGS["cfg3"], nc=nc)
+    rng = np.random.default_rng(nc)
+    hd = synth.planted_head(cfg, 3000)
+    for l in range(3):                                   # spread the planted class-0/1 evidence over all classes
+        x = hd["levels"][l]
+        perm = rng.integers(0, nc, x.shape[1:])
+        cls_part = x[64:].copy()
+        top = cls_part.max(axis=0)
+        cls_part[:] = rng.normal(-7, 1, cls_part.shape)
+        np.put_along_axis(cls_part, perm[None], top[None], axis=0)
+        x[64:] = cls_part
+    ec = EngineConfig.for_workload(cfg, helpers.load_calib(), max_batch=1)
+    eng = InspectionEngine(ec)
+    dets, counts, results, _ = eng.post_measure(*[dev(x[None]) for x in hd["levels"]], dev(hd["coef"][None]),
+                                                dev(hd["proto"][None]))
+    torch.cuda.synchronize()
+    sp = post_spec.postprocess_spec(hd["levels"], hd["coef"], cfg.conf, cfg.iou, cfg.max_det, nc, cfg.LH, cfg.LW,
+                                    cfg.frame_h, cfg.frame_w)
+    n = int(counts[0])
+    d = eng.dets_to_numpy(dets)[0, :n]
+    assert n == len(sp["keep_anchor"]) and n > 10
+    assert np.array_equal(d["anchor"], sp["keep_anchor"]) and np.array_equal(d["cls"], sp["cls"])
+    assert np.array_equal(d["box_lb"].view(np.uint32), sp["box_lb"].view(np.uint32))
