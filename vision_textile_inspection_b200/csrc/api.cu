@@ -274,7 +274,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     alloc((void**)&h->d_env_frame, sizeof(int32_t) * B * fw);
     alloc((void**)&h->d_flags, sizeof(int32_t) * B);
     h->units_per_det = ((g.ph + 1 + VTI_K4_UR - 1) / VTI_K4_UR) * ((g.pw + 1 + VTI_K4_UC - 1) / VTI_K4_UC);
-    alloc((void**)&h->d_units, sizeof(uint2) * B * p->max_det * h->units_per_det);
+    alloc((void**)&h->d_units, sizeof(uint4) * B * p->max_det * h->units_per_det);
     if (e != cudaSuccess) {
         vti_set_error(std::string("vti_create: cudaMalloc: ") + cudaGetErrorString(e));
         vti_destroy(h);

@@ -53,7 +53,7 @@ struct K3Args {
     int env_init;
     int ph, pw, all_dets, units_per_det;
     int32_t* unit_count;        // one counter for the whole batch
-    uint2* units;
+    uint4* units;
 };
 
 // torchvision's test is `float32(inter / uni) > iou` with iou a double.  Let T be the smallest float32 above iou and
@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     // ---- 3. epilogue
     vti_det* __restrict__ dets = a.dets + (size_t)b * a.max_det;
     int4* s_win = reinterpret_cast<int4*>(s_kbox);        // the sweep is over: s_kbox is reused for the crop windows
+    unsigned* s_kflags = reinterpret_cast<unsigned*>(s_karea);   // ... and s_karea for the routing flags
     int nu = 0;                                            // K4 work units of this thread's detection
     __syncthreads();
     if (tid < nk) {
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         const bool wanted = a.all_dets || ((f & VTI_F_IN_ROI) && (f & (VTI_F_STITCH | VTI_F_FABRIC)));
         const VtiWindow w = vti_det_window(d.box_lb, a.ph, a.pw);
         s_win[tid] = make_int4(w.cx_lo, w.cx_hi, w.cy_lo, w.cy_hi);
+        s_kflags[tid] = f;
         if (wanted && !w.empty)
             nu = ((w.cy_hi - w.cy_lo + 2 + VTI_K4_UR - 1) / VTI_K4_UR) * ((w.cx_hi - w.cx_lo + 2 + VTI_K4_UC - 1) / VTI_K4_UC);
     }
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         const int total = s_wsum[31];
         if (tid == 0) s_ubase = total ? atomicAdd(a.unit_count, total) : 0;
         __syncthreads();
-        uint2* __restrict__ units = a.units + s_ubase;
+        uint4* __restrict__ units = a.units + s_ubase;
         for (int i = tid; i < total; i += K3_THREADS) {
             int lo = 0, hi = nk - 1;                       // last detection with s_upre[k] <= i
             while (lo < hi) {
@@ -375,7 +377,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
             const int4 w = s_win[k];
             const int nb = (w.y - w.x + 2 + VTI_K4_UC - 1) / VTI_K4_UC;
             const int br = local / nb, bc = local - br * nb;
-            units[i] = make_uint2((unsigned)b | ((unsigned)k << 16), (unsigned)br | ((unsigned)bc << 16));
+            const unsigned fabric = ((s_kflags[k] & VTI_F_FABRIC) && (s_kflags[k] & VTI_F_IN_ROI)) ? 0x8000u : 0u;
+            units[i] = make_uint4((unsigned)b | fabric | ((unsigned)k << 16), (unsigned)br | ((unsigned)bc << 16),
+                                  (unsigned)w.x | ((unsigned)w.z << 16), (unsigned)w.y | ((unsigned)w.w << 16));
         }
     }
     // coefficient gather: [32][A] strided -> compact [nk][32]

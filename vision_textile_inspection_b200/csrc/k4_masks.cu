@@ -40,7 +40,7 @@ struct K4Args {
     const float* proto;         // [B][32][ph][pw]
     vti_det* dets;              // [B][max_det]
     const float* det_coef;      // [B][max_det][32]
-    const uint2* units;
+    const uint4* units;
     const int32_t* unit_count;
     AxisLut ly, lx;
     int32_t* env;               // [B][LW] frame-row envelope per letterbox column
@@ -70,12 +70,13 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
     const unsigned long long plane_bytes = plane * sizeof(float);
 
     for (int u = blockIdx.x * NWARP + warp; u < total; u += nwarps) {
-        const uint2 un = __ldg(a.units + u);
-        const int b = (int)(un.x & 0xFFFFu), k = (int)(un.x >> 16), br = (int)(un.y & 0xFFFFu), bc = (int)(un.y >> 16);
+        const uint4 un = __ldg(a.units + u);
+        const int b = (int)(un.x & 0x7FFFu), k = (int)(un.x >> 16), br = (int)(un.y & 0xFFFFu), bc = (int)(un.y >> 16);
+        const bool fabric = (un.x & 0x8000u) != 0u;
         vti_det* __restrict__ det = a.dets + (size_t)b * a.max_det + k;
-        const VtiWindow w = vti_det_window(det->box_lb, a.ph, a.pw);
-        const unsigned f = det->flags;
-        const bool fabric = (f & VTI_F_FABRIC) && (f & VTI_F_IN_ROI);
+        VtiWindow w;                                        // the crop window travels in the unit record
+        w.cx_lo = (int)(un.z & 0xFFFFu); w.cy_lo = (int)(un.z >> 16);
+        w.cx_hi = (int)(un.w & 0xFFFFu); w.cy_hi = (int)(un.w >> 16);
         // cells of this unit (global cell coordinates) and their corner rectangle
         const int R0 = w.cy_lo + br * UR, R1 = min(R0 + UR - 1, w.cy_hi + 1);
         const int C0 = w.cx_lo + bc * UC, C1 = min(C0 + UC - 1, w.cx_hi + 1);

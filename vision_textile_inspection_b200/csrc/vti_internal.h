@@ -57,7 +57,8 @@ struct vti_handle {
     int32_t* d_env;                                // [B][LW]  envelope in frame rows at letterbox columns
     int32_t* d_env_frame;                          // [B][frame_w]
     int32_t* d_flags;                              // [B] overflow etc.
-    uint2* d_units;                                // K4 work units (frame | det << 16, block row | block col << 16)
+    uint4* d_units;                                // K4 work units: (frame | fabric << 15 | det << 16, block row | block col << 16,
+                                                   //                 cx_lo | cy_lo << 16, cx_hi | cy_hi << 16)
     int units_per_det;                             // capacity per detection slot
     // ---- host-buffer path
     cudaStream_t own_stream, copy_stream;
