@@ -420,3 +420,20 @@ def test_decode_nms_other_class_counts(nc):
     assert n == len(sp["keep_anchor"]) and n > 10
     assert np.array_equal(d["anchor"], sp["keep_anchor"]) and np.array_equal(d["cls"], sp["cls"])
     assert np.array_equal(d["box_lb"].view(np.uint32), sp["box_lb"].view(np.uint32))
+
+
+def test_k4_tma_form_matches_ldg_form(monkeypatch):
+    """The opt-in TMA form of K4 (cp.async.bulk.tensor boxes + mbarrier double buffering; slower on B200, kept as a
+    measured experiment) must produce byte-identical records to the default LDG form."""
+    cfg = synth.CONFIGS["cfg2"]
+    seeds = [2000, 2001, 2002]
+    monkeypatch.delenv("VTI_K4_TMA", raising=False)
+    _, _, d1, c1, r1, m1 = run_gpu(cfg, seeds, export_masks=True)
+    monkeypatch.setenv("VTI_K4_TMA", "1")
+    _, _, d2, c2, r2, m2 = run_gpu(cfg, seeds, export_masks=True)
+    assert np.array_equal(c1, c2)
+    for b in range(len(seeds)):
+        n = int(c1[b])
+        assert torch.equal(m1[b, :n], m2[b, :n])                   # (slots past the count are never written)
+        assert d1[b, :n].tobytes() == d2[b, :n].tobytes()
+    assert r1.tobytes() == r2.tobytes()

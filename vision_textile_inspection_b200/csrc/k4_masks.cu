@@ -26,6 +26,8 @@
 #include <climits>
 #include <cstdlib>
 
+#include <cuda.h>
+
 #include "vti_internal.h"
 
 namespace {
@@ -57,6 +59,116 @@ __global__ void k4_zero_masks_kernel(uint32_t* masks, const int32_t* counts, int
     for (size_t i = threadIdx.x; i < n4; i += blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Phases 2 and 3 of a unit: classify the interpolation cells from the corner values `sc` (pitch SCW), accumulate the
+// nearest-resize statistics, flush the unit's fabric envelope and reduce across the warp.
+template <bool EXPORT>
+__device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_det* __restrict__ det, bool fabric, int R0,
+                                           int C0, int nr, int ncw, const float* sc, int* envw, int lane) {
+    const int ex0 = 4 * C0 - 2;                            // first output column of the unit
+    // (2) cells
+    const int ncc = ncw - 1;
+    const float inv_ncc = 1.0f / (float)ncc;
+    long long m00 = 0, m10 = 0, m01 = 0;
+    int cmin = INT_MAX, cmax = -1;
+    uint32_t* __restrict__ mrow = EXPORT ? a.masks + ((size_t)b * a.max_det + k) * a.LH * (a.LW / 32) : nullptr;
+    for (int i = lane; i < (nr - 1) * ncc; i += 32) {
+        const int r = (int)(((float)i + 0.5f) * inv_ncc), c = i - r * ncc;
+        // cell (R, C) covers output rows 4R-2 .. 4R+1 and cols 4C-2 .. 4C+1, clipped to the image
+        const int cy_first = 4 * (R0 + r) - 2, cx_first = 4 * (C0 + c) - 2;
+        const int ya = max(cy_first, 0), yb = min(cy_first + 3, a.LH - 1);
+        const int xa = max(cx_first, 0), xb = min(cx_first + 3, a.LW - 1);
+        if (ya > yb || xa > xb) continue;
+        const float c00 = sc[r * SCW + c], c01 = sc[r * SCW + c + 1];
+        const float c10 = sc[(r + 1) * SCW + c], c11 = sc[(r + 1) * SCW + c + 1];
+        const float vmin = fminf(fminf(c00, c01), fminf(c10, c11));
+        const float vmax = fmaxf(fmaxf(c00, c01), fmaxf(c10, c11));
+        if (vmin > 0.5f + MARGIN) {
+            // fully set: closed form from the prefix sums of the nearest-resize multiplicity tables
+            const int f_cy = a.ly.pc[yb + 1] - a.ly.pc[ya], f_sy = a.ly.ps[yb + 1] - a.ly.ps[ya];
+            const int f_cx = a.lx.pc[xb + 1] - a.lx.pc[xa], f_sx = a.lx.ps[xb + 1] - a.lx.ps[xa];
+            m00 += f_cy * f_cx; m10 += f_cy * f_sx; m01 += f_sy * f_cx;
+            if (f_cy > 0 && f_cx > 0) {
+                cmin = min(cmin, a.lx.next_first[xa]); cmax = max(cmax, a.lx.prev_last[xb]);
+                if (fabric) {
+                    const int f_env = a.upper ? a.ly.next_first[ya] : a.ly.prev_last[yb];
+                    for (int X = xa; X <= xb; ++X)
+                        if (a.lx.cnt[X] > 0) {
+                            if (a.upper) atomicMin(&envw[X - ex0], f_env);
+                            else atomicMax(&envw[X - ex0], f_env);
+                        }
+                }
+            }
+            if (EXPORT) {
+                const unsigned long long bits = ((1ull << (xb - xa + 1)) - 1ull) << (xa & 31);
+                for (int Y = ya; Y <= yb; ++Y) {
+                    uint32_t* wp = mrow + (size_t)Y * (a.LW / 32) + (xa >> 5);
+                    atomicOr(wp, (unsigned)bits);
+                    if ((unsigned)(bits >> 32)) atomicOr(wp + 1, (unsigned)(bits >> 32));
+                }
+            }
+        } else if (vmax >= 0.5f - MARGIN) {
+            // boundary cell: evaluate its pixels (torch upsample_bilinear2d, align_corners=False, scale 1/4)
+            for (int Y = ya; Y <= yb; ++Y) {
+                const float ly1 = (float)(2 * (Y - cy_first) + 1) * 0.125f;
+                const int cY = a.ly.cnt[Y], sY = a.ly.sum[Y];
+                unsigned long long rowbits = 0ull;
+                for (int X = xa; X <= xb; ++X) {
+                    const float lx1 = (float)(2 * (X - cx_first) + 1) * 0.125f;
+                    const float top = (1.0f - lx1) * c00 + lx1 * c01;
+                    const float bot = (1.0f - lx1) * c10 + lx1 * c11;
+                    const float v = (1.0f - ly1) * top + ly1 * bot;
+                    if (v > 0.5f) {
+                        rowbits |= 1ull << ((X - xa) + (xa & 31));
+                        const int cX = a.lx.cnt[X];
+                        m00 += cY * cX; m10 += cY * a.lx.sum[X]; m01 += sY * cX;
+                        if (cY > 0 && cX > 0) {
+                            cmin = min(cmin, a.lx.first[X]);
+                            cmax = max(cmax, a.lx.last[X]);
+                            if (fabric) {
+                                if (a.upper) atomicMin(&envw[X - ex0], a.ly.first[Y]);
+                                else atomicMax(&envw[X - ex0], a.ly.last[Y]);
+                            }
+                        }
+                    }
+                }
+                if (EXPORT && rowbits) {
+                    uint32_t* wp = mrow + (size_t)Y * (a.LW / 32) + (xa >> 5);
+                    if ((unsigned)rowbits) atomicOr(wp, (unsigned)rowbits);
+                    if ((unsigned)(rowbits >> 32)) atomicOr(wp + 1, (unsigned)(rowbits >> 32));
+                }
+            }
+        }
+    }
+    if (fabric) {                                       // one RED per touched column and unit
+        __syncwarp();
+        int32_t* __restrict__ env = a.env + (size_t)b * a.LW;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int ev = envw[lane + 32 * hh], X = ex0 + lane + 32 * hh;
+            if (a.upper) { if (ev != INT_MAX) atomicMin(env + X, ev); }
+            else { if (ev >= 0) atomicMax(env + X, ev); }
+        }
+    }
+    // (3) warp reduction, one set of global atomics per unit
+    if (__any_sync(0xffffffffu, m00 > 0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m00 += __shfl_xor_sync(0xffffffffu, m00, o);
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        cmin = __reduce_min_sync(0xffffffffu, cmin);
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&det->m00, (unsigned long long)m00);
+            atomicAdd((unsigned long long*)&det->m10, (unsigned long long)m10);
+            atomicAdd((unsigned long long*)&det->m01, (unsigned long long)m01);
+            atomicMin(&det->col_min, cmin);
+            atomicMax(&det->col_max, cmax);
+        }
+    }
+}
+
 template <bool EXPORT>
 __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a) {
     __shared__ float s_c[NWARP][(UR + 1) * SCW];
@@ -85,7 +197,6 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
         __syncwarp();
         s_coef[warp][lane] = __ldg(a.det_coef + ((size_t)b * a.max_det + k) * VTI_NM + lane);
         if (fabric) { s_envw[warp][lane] = a.upper ? INT_MAX : -1; s_envw[warp][lane + 32] = a.upper ? INT_MAX : -1; }
-        const int ex0 = 4 * C0 - 2;                        // first output column of the unit
         const float* __restrict__ proto = a.proto + (size_t)b * VTI_NM * plane;
         __syncwarp();
         // (1) logits -> sigmoid -> crop over the corner rectangle (replicate-clamped at the plane border)
@@ -115,114 +226,158 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a)
             sc[r * SCW + c] = v;
         }
         __syncwarp();
-        // (2) cells
-        const int ncc = ncw - 1;
-        const float inv_ncc = 1.0f / (float)ncc;
-        long long m00 = 0, m10 = 0, m01 = 0;
-        int cmin = INT_MAX, cmax = -1;
-        uint32_t* __restrict__ mrow = EXPORT ? a.masks + ((size_t)b * a.max_det + k) * a.LH * (a.LW / 32) : nullptr;
-        for (int i = lane; i < (nr - 1) * ncc; i += 32) {
-            const int r = (int)(((float)i + 0.5f) * inv_ncc), c = i - r * ncc;
-            // cell (R, C) covers output rows 4R-2 .. 4R+1 and cols 4C-2 .. 4C+1, clipped to the image
-            const int cy_first = 4 * (R0 + r) - 2, cx_first = 4 * (C0 + c) - 2;
-            const int ya = max(cy_first, 0), yb = min(cy_first + 3, a.LH - 1);
-            const int xa = max(cx_first, 0), xb = min(cx_first + 3, a.LW - 1);
-            if (ya > yb || xa > xb) continue;
-            const float c00 = sc[r * SCW + c], c01 = sc[r * SCW + c + 1];
-            const float c10 = sc[(r + 1) * SCW + c], c11 = sc[(r + 1) * SCW + c + 1];
-            const float vmin = fminf(fminf(c00, c01), fminf(c10, c11));
-            const float vmax = fmaxf(fmaxf(c00, c01), fmaxf(c10, c11));
-            if (vmin > 0.5f + MARGIN) {
-                // fully set: closed form from the prefix sums of the nearest-resize multiplicity tables
-                const int f_cy = a.ly.pc[yb + 1] - a.ly.pc[ya], f_sy = a.ly.ps[yb + 1] - a.ly.ps[ya];
-                const int f_cx = a.lx.pc[xb + 1] - a.lx.pc[xa], f_sx = a.lx.ps[xb + 1] - a.lx.ps[xa];
-                m00 += f_cy * f_cx; m10 += f_cy * f_sx; m01 += f_sy * f_cx;
-                if (f_cy > 0 && f_cx > 0) {
-                    cmin = min(cmin, a.lx.next_first[xa]); cmax = max(cmax, a.lx.prev_last[xb]);
-                    if (fabric) {
-                        const int f_env = a.upper ? a.ly.next_first[ya] : a.ly.prev_last[yb];
-                        for (int X = xa; X <= xb; ++X)
-                            if (a.lx.cnt[X] > 0) {
-                                if (a.upper) atomicMin(&s_envw[warp][X - ex0], f_env);
-                                else atomicMax(&s_envw[warp][X - ex0], f_env);
-                            }
-                    }
-                }
-                if (EXPORT) {
-                    const unsigned long long bits = ((1ull << (xb - xa + 1)) - 1ull) << (xa & 31);
-                    for (int Y = ya; Y <= yb; ++Y) {
-                        uint32_t* wp = mrow + (size_t)Y * (a.LW / 32) + (xa >> 5);
-                        atomicOr(wp, (unsigned)bits);
-                        if ((unsigned)(bits >> 32)) atomicOr(wp + 1, (unsigned)(bits >> 32));
-                    }
-                }
-            } else if (vmax >= 0.5f - MARGIN) {
-                // boundary cell: evaluate its pixels (torch upsample_bilinear2d, align_corners=False, scale 1/4)
-                for (int Y = ya; Y <= yb; ++Y) {
-                    const float ly1 = (float)(2 * (Y - cy_first) + 1) * 0.125f;
-                    const int cY = a.ly.cnt[Y], sY = a.ly.sum[Y];
-                    unsigned long long rowbits = 0ull;
-                    for (int X = xa; X <= xb; ++X) {
-                        const float lx1 = (float)(2 * (X - cx_first) + 1) * 0.125f;
-                        const float top = (1.0f - lx1) * c00 + lx1 * c01;
-                        const float bot = (1.0f - lx1) * c10 + lx1 * c11;
-                        const float v = (1.0f - ly1) * top + ly1 * bot;
-                        if (v > 0.5f) {
-                            rowbits |= 1ull << ((X - xa) + (xa & 31));
-                            const int cX = a.lx.cnt[X];
-                            m00 += cY * cX; m10 += cY * a.lx.sum[X]; m01 += sY * cX;
-                            if (cY > 0 && cX > 0) {
-                                cmin = min(cmin, a.lx.first[X]);
-                                cmax = max(cmax, a.lx.last[X]);
-                                if (fabric) {
-                                    if (a.upper) atomicMin(&s_envw[warp][X - ex0], a.ly.first[Y]);
-                                    else atomicMax(&s_envw[warp][X - ex0], a.ly.last[Y]);
-                                }
-                            }
-                        }
-                    }
-                    if (EXPORT && rowbits) {
-                        uint32_t* wp = mrow + (size_t)Y * (a.LW / 32) + (xa >> 5);
-                        if ((unsigned)rowbits) atomicOr(wp, (unsigned)rowbits);
-                        if ((unsigned)(rowbits >> 32)) atomicOr(wp + 1, (unsigned)(rowbits >> 32));
-                    }
-                }
-            }
+        unit_cells<EXPORT>(a, b, k, det, fabric, R0, C0, nr, ncw, sc, s_envw[warp], lane);
+    }
+}
+
+
+// ====================================================================================================================
+// TMA form of the unit kernel (opt-in, kept as a measured experiment: see vti_launch_k4).  A unit's prototype corner block is a 3-D box {TB_W columns, UR+1 rows, 32 channels} of
+// the [B*32][ph][pw] prototype tensor: ONE cp.async.bulk.tensor (TMA) brings it into shared memory, where the LDG
+// form needs 32 loads + 64 address instructions per lane and iteration.  Each warp double-buffers: the box of its next
+// unit is in flight (mbarrier with the byte count) while it contracts, classifies and reduces the current one, so the
+// L2/HBM latency that bounded the LDG form (issue slots 47-60 % used) is off the critical path.  Out-of-plane parts of
+// a box are zero-filled by the TMA unit and never read: the replicate clamp of the upsample is applied to the
+// shared-memory index.
+// ====================================================================================================================
+constexpr int TB_W = 24;                           // box columns: the box starts at the 16-byte-aligned column at or below
+                                                   // C0 - 1 (TMA needs 16-byte-aligned row starts), so 3 + UC + 1 = 20 <= 24
+constexpr int TB_H = UR + 1;
+constexpr int TB_FLOATS = VTI_NM * TB_H * TB_W;
+constexpr int TB_BYTES = TB_FLOATS * 4;            // 15 360 with UR = 4
+constexpr int T_WARPS = 3;                         // warps per CTA: 3 x 2 buffers x 15 KB = 90 KB, two CTAs per SM
+static_assert(TB_BYTES % 128 == 0, "TMA destination alignment");
+
+__device__ __forceinline__ unsigned k4_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct UnitGeo {
+    int b, k, R0, C0, nr, ncw;
+    bool fabric;
+    VtiWindow w;
+};
+__device__ __forceinline__ UnitGeo unit_geo(const uint4 un) {
+    UnitGeo g;
+    g.b = (int)(un.x & 0x7FFFu); g.k = (int)(un.x >> 16);
+    g.fabric = (un.x & 0x8000u) != 0u;
+    const int br = (int)(un.y & 0xFFFFu), bc = (int)(un.y >> 16);
+    g.w.cx_lo = (int)(un.z & 0xFFFFu); g.w.cy_lo = (int)(un.z >> 16);
+    g.w.cx_hi = (int)(un.w & 0xFFFFu); g.w.cy_hi = (int)(un.w >> 16);
+    g.w.empty = false;
+    g.R0 = g.w.cy_lo + br * UR; g.C0 = g.w.cx_lo + bc * UC;
+    const int R1 = min(g.R0 + UR - 1, g.w.cy_hi + 1), C1 = min(g.C0 + UC - 1, g.w.cx_hi + 1);
+    g.nr = R1 - g.R0 + 2; g.ncw = C1 - g.C0 + 2;
+    return g;
+}
+
+template <bool EXPORT>
+__global__ void __launch_bounds__(T_WARPS * 32, 2) k4_tma_kernel(const __grid_constant__ CUtensorMap tmap, const K4Args a) {
+    extern __shared__ __align__(128) float s_box[];                     // [T_WARPS][2][TB_FLOATS]
+    __shared__ __align__(8) unsigned long long s_bar[T_WARPS][2];
+    __shared__ float s_c[T_WARPS][(UR + 1) * SCW];
+    __shared__ __align__(16) float s_coef[T_WARPS][VTI_NM];
+    __shared__ int s_envw[T_WARPS][4 * UC];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = *a.unit_count;
+    const int nwarps = gridDim.x * T_WARPS;
+    int u = blockIdx.x * T_WARPS + warp;
+    if (u >= total) return;                                             // (no block-wide barrier anywhere below)
+    float* buf0 = s_box + (size_t)warp * 2 * TB_FLOATS;
+    float* sc = s_c[warp];
+    const unsigned long long tmap_addr = reinterpret_cast<unsigned long long>(&tmap);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" :: "r"(k4_smem_u32(&s_bar[warp][0])) : "memory");
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" :: "r"(k4_smem_u32(&s_bar[warp][1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](const UnitGeo& g, int slot) {                      // lane 0: arm the barrier, start the box copy
+        const unsigned bar = k4_smem_u32(&s_bar[warp][slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)TB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     :: "r"(k4_smem_u32(buf0 + (size_t)slot * TB_FLOATS)), "l"(tmap_addr), "r"((g.C0 - 1) & ~3), "r"(g.R0 - 1),
+                        "r"(g.b * VTI_NM), "r"(bar) : "memory");
+    };
+    UnitGeo g = unit_geo(__ldg(a.units + u));
+    if (lane == 0) issue(g, 0);
+    unsigned parity0 = 0u, parity1 = 0u;
+    for (int it = 0;; ++it) {
+        const int cur = it & 1;
+        const int un = u + nwarps;
+        const bool more = un < total;
+        UnitGeo gn = g;
+        if (more) {
+            gn = unit_geo(__ldg(a.units + un));
+            if (lane == 0) issue(gn, cur ^ 1);                          // that buffer was consumed one iteration ago
         }
-        if (fabric) {                                       // one RED per touched column and unit
-            __syncwarp();
-            int32_t* __restrict__ env = a.env + (size_t)b * a.LW;
+        // this unit's coefficients and envelope scratch while its box lands
+        vti_det* __restrict__ det = a.dets + (size_t)g.b * a.max_det + g.k;
+        s_coef[warp][lane] = __ldg(a.det_coef + ((size_t)g.b * a.max_det + g.k) * VTI_NM + lane);
+        if (g.fabric) { s_envw[warp][lane] = a.upper ? INT_MAX : -1; s_envw[warp][lane + 32] = a.upper ? INT_MAX : -1; }
+        {
+            const unsigned bar = k4_smem_u32(&s_bar[warp][cur]), par = cur ? parity1 : parity0;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "W_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra D_%=;\n\t"
+                "bra W_%=;\n\t"
+                "D_%=:\n\t}"
+                :: "r"(bar), "r"(par) : "memory");
+            if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+        }
+        __syncwarp();
+        // (1) logits -> sigmoid -> crop over the corner rectangle, prototype values from the box in shared memory
+        const float* box = buf0 + (size_t)cur * TB_FLOATS;
+        const float inv_ncw = 1.0f / (float)g.ncw;
+        for (int i = lane; i < g.nr * g.ncw; i += 32) {
+            const int r = (int)(((float)i + 0.5f) * inv_ncw), c = i - r * g.ncw;
+            const int py = min(max(g.R0 - 1 + r, 0), a.ph - 1), px = min(max(g.C0 - 1 + c, 0), a.pw - 1);
+            float v = 0.0f;
+            if (py >= g.w.cy_lo && py <= g.w.cy_hi && px >= g.w.cx_lo && px <= g.w.cx_hi) {
+                const float* src = box + (py - (g.R0 - 1)) * TB_W + (px - ((g.C0 - 1) & ~3));   // replicate clamp on the index
+                float acc = 0.0f;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int ev = s_envw[warp][lane + 32 * hh], X = ex0 + lane + 32 * hh;
-                if (a.upper) { if (ev != INT_MAX) atomicMin(env + X, ev); }
-                else { if (ev >= 0) atomicMax(env + X, ev); }
+                for (int q = 0; q < VTI_NM; q += 4) {
+                    const float4 cf = *reinterpret_cast<const float4*>(&s_coef[warp][q]);
+                    acc = fmaf(cf.x, src[(q + 0) * TB_H * TB_W], acc); acc = fmaf(cf.y, src[(q + 1) * TB_H * TB_W], acc);
+                    acc = fmaf(cf.z, src[(q + 2) * TB_H * TB_W], acc); acc = fmaf(cf.w, src[(q + 3) * TB_H * TB_W], acc);
+                }
+                v = 1.0f / (1.0f + expf(-acc));
             }
+            sc[r * SCW + c] = v;
         }
-        // (3) warp reduction, one set of global atomics per unit
-        if (__any_sync(0xffffffffu, m00 > 0)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                m00 += __shfl_xor_sync(0xffffffffu, m00, o);
-                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-            }
-            cmin = __reduce_min_sync(0xffffffffu, cmin);
-            cmax = __reduce_max_sync(0xffffffffu, cmax);
-            if (lane == 0) {
-                atomicAdd((unsigned long long*)&det->m00, (unsigned long long)m00);
-                atomicAdd((unsigned long long*)&det->m10, (unsigned long long)m10);
-                atomicAdd((unsigned long long*)&det->m01, (unsigned long long)m01);
-                atomicMin(&det->col_min, cmin);
-                atomicMax(&det->col_max, cmax);
-            }
-        }
+        __syncwarp();
+        unit_cells<EXPORT>(a, g.b, g.k, det, g.fabric, g.R0, g.C0, g.nr, g.ncw, sc, s_envw[warp], lane);
+        __syncwarp();                                                   // everyone is done with box[cur], s_c, s_coef
+        if (!more) break;
+        g = gn; u = un;
     }
 }
 
 }  // namespace
 
-int vti_k4_prepare() { return VTI_OK; }
+typedef CUresult (*vti_encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static vti_encode_tiled_t g_encode_tiled = nullptr;
+constexpr size_t K4_TMA_SMEM = (size_t)T_WARPS * 2 * TB_BYTES;
+
+int vti_k4_prepare() {
+    // cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<vti_encode_tiled_t>(fn);
+        else
+            cudaGetLastError();
+    }
+    VTI_CUDA(cudaFuncSetAttribute(k4_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K4_TMA_SMEM));
+    VTI_CUDA(cudaFuncSetAttribute(k4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K4_TMA_SMEM));
+    return VTI_OK;
+}
 
 int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const int32_t* counts, uint32_t* masks,
                   cudaStream_t s) {
@@ -237,15 +392,34 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
     a.masks = masks;
     a.LH = h->g.LH; a.LW = h->g.LW; a.ph = h->g.ph; a.pw = h->g.pw; a.max_det = h->p.max_det;
     a.upper = (h->p.variant == 1);
-    // grid-stride over the device-side unit list: four 8-warp CTAs per SM
-    const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : 4) * h->num_sms;
     if (masks) {
         const size_t wpm = (size_t)a.LH * (a.LW / 32);
         k4_zero_masks_kernel<<<dim3(a.max_det, B), 256, 0, s>>>(masks, counts, a.max_det, wpm);
         h->launches++;
-        k4_units_kernel<true><<<grid, K4_THREADS, 0, s>>>(a);
+    }
+    // TMA form: the prototype tensor as [B*32][ph][pw] float32, boxes of {TB_W, UR+1, 32}
+    CUtensorMap tmap;
+    // OPT-IN (VTI_K4_TMA=1): measured on B200 the TMA form is 2x SLOWER than the LDG form (137 vs 70 us per 64 frames):
+    // a unit's box is 128 rows of 96 bytes, and the TMA unit's per-row request rate, not bandwidth or latency, bounds it.
+    bool tma = g_encode_tiled && getenv("VTI_K4_TMA") && (reinterpret_cast<uintptr_t>(proto) & 15) == 0 &&
+               (a.pw % 4) == 0;
+    if (tma) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)a.pw, (cuuint64_t)a.ph, (cuuint64_t)VTI_NM * B};
+        const cuuint64_t gstr[2] = {(cuuint64_t)a.pw * 4, (cuuint64_t)a.pw * a.ph * 4};
+        const cuuint32_t box[3] = {TB_W, TB_H, VTI_NM}, estr[3] = {1, 1, 1};
+        tma = g_encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(proto), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (tma) {
+        const int grid = 2 * h->num_sms;                   // two 4-warp CTAs per SM, grid-stride over the unit list
+        if (masks) k4_tma_kernel<true><<<grid, T_WARPS * 32, K4_TMA_SMEM, s>>>(tmap, a);
+        else k4_tma_kernel<false><<<grid, T_WARPS * 32, K4_TMA_SMEM, s>>>(tmap, a);
     } else {
-        k4_units_kernel<false><<<grid, K4_THREADS, 0, s>>>(a);
+        // LDG form (no driver entry point, unaligned prototype pointer): four 8-warp CTAs per SM
+        const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : 4) * h->num_sms;
+        if (masks) k4_units_kernel<true><<<grid, K4_THREADS, 0, s>>>(a);
+        else k4_units_kernel<false><<<grid, K4_THREADS, 0, s>>>(a);
     }
     h->launches++;
     VTI_CUDA(cudaGetLastError());
