@@ -633,7 +633,7 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
             // Leave room on every SM for the post kernels that run beside K1 (two streams): at most 4 resident K1 CTAs.
             // Measured: 5 CTAs/SM make K1 alone 5 % faster and the whole pre || post step 8 % slower.
             if (getenv("VTI_K1_SMEM_FLOOR")) smem = std::max(smem, (size_t)atoi(getenv("VTI_K1_SMEM_FLOOR")));
-            else smem = std::max(smem, (size_t)(46 * 1024 + 512));
+            else if (und_ix) smem = std::max(smem, (size_t)(46 * 1024 + 512));     // (measured with the remap path)
             if (smem <= 110 * 1024) {
                 h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
                 h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;
