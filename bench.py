@@ -24,6 +24,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# stdout carries exactly ONE JSON line: libraries that chat on file descriptor 1 (NCCL prints its version banner there)
+# are sent to stderr, the line itself goes to the saved descriptor.
+REAL_STDOUT = sys.stdout
+
+
+def _protect_stdout():
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 METRIC = "inspected frames/sec (pre+post+measure)"
 UNIT = "frames/s"
 
@@ -212,7 +224,7 @@ def run_reference(args, cfg, rank, world):
                                    f"threads={cores})"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
 def run_b200(args, cfg, rank, world, local_rank):
@@ -224,9 +236,6 @@ def run_b200(args, cfg, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (this image's default): keep stdout = one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     calib = load_reference_calibration()
     B = cfg.batch if args.batch is None else args.batch
@@ -450,7 +459,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -467,6 +476,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
     args = ap.parse_args()
+    _protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
