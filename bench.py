@@ -250,13 +250,20 @@ def run_b200(args, cfg, rank, world, local_rank):
     d_lv = [l.to(dev) for l in host_lv]
     d_coef, d_proto = host["coef"].to(dev), host["proto"].to(dev)
     net_in = torch.empty((B, 3, eng.LH, eng.LW), dtype=torch.float32, device=dev)
-    packed, outs = shard.alloc_packed(B, cfg.max_det, dev)            # records + results + counts in one buffer: one gather
+    # records + results + counts of a step live in ONE buffer (one all-gather); two such buffers alternate so that the
+    # gather of step i (its own stream) runs under the kernels of step i+1
+    bufs = [shard.alloc_packed(B, cfg.max_det, dev) for _ in range(2)]
+    packed, outs = bufs[0]
+    gathered = [torch.empty((world * bufs[0][0].numel(),), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     in_bytes = (d_frames.numel() + 4 * (sum(l.numel() for l in d_lv) + d_coef.numel() + d_proto.numel()))
     out_bytes = 4 * net_in.numel()
 
     # Pre (K1) and post+measure (K2..K5) of one batch are independent -- the backbone sits between them -- so they are
     # issued on two streams: the latency-bound per-frame CTAs of K3/K5 run under the streaming K1.
     s_pre, s_post = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)   # post CTAs win free SM slots
+    s_gather = torch.cuda.Stream(dev, priority=-1)
+    ev_gather = [None, None]
+    state = {"i": 0}
 
     def step(overlap=True):
         """One pass of the hot path over one batch.  overlap=True: K1 goes to s_pre, K2..K5 (+ the record gather) to
@@ -268,10 +275,19 @@ def run_b200(args, cfg, rank, world, local_rank):
             if world > 1:
                 shard.gather_packed(packed)
             return
+        k = state["i"] & 1
+        state["i"] += 1
+        pk, ot = bufs[k]
         with torch.cuda.stream(s_post):
-            dets, counts, results, _ = eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=outs)
-            if world > 1:
-                shard.gather_packed(packed)
+            if world > 1 and ev_gather[k] is not None:
+                s_post.wait_event(ev_gather[k])                # buffer k was gathered two steps ago
+            eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=ot)
+        if world > 1:
+            s_gather.wait_stream(s_post)
+            with torch.cuda.stream(s_gather):
+                dist.all_gather_into_tensor(gathered[k], pk)   # ranks in frame order; shard.unpack_packed gives the views
+                ev_gather[k] = torch.cuda.Event()
+                ev_gather[k].record(s_gather)
         with torch.cuda.stream(s_pre):
             eng.preprocess(d_frames, out=net_in)
 
@@ -279,11 +295,13 @@ def run_b200(args, cfg, rank, world, local_rank):
         cur = torch.cuda.current_stream(dev)
         s_pre.wait_stream(cur)
         s_post.wait_stream(cur)
+        s_gather.wait_stream(cur)
 
     def join():
         cur = torch.cuda.current_stream(dev)
         cur.wait_stream(s_pre)
         cur.wait_stream(s_post)
+        cur.wait_stream(s_gather)
 
     def barrier():
         if world > 1:
@@ -439,7 +457,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "net_in": [cfg.LW, cfg.LH], "anchors": cfg.anchors, "undistort": cfg.undistort,
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                   "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority), joined at the ends of the timed region",
+                   "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority) + the record all-gather on a third (double-buffered records), joined at the ends of the timed region",
                    "clock_sampling": "nvidia-smi every 100 ms over the timed steps + an untimed continuation of the same loop",
                    "status_ok_frames": int((res["status"] == 0).sum())},
         "clocks": clocks,
