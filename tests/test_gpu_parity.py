@@ -284,6 +284,21 @@ def test_process_host_matches_device_path(calib):
         assert np.array_equal(dets[b, :counts[b]]["anchor"], d2[b, :counts[b]]["anchor"])
 
 
+def test_process_host_zero_copy_pinned_buffers(calib):
+    """Pinned (device-mapped) head tensors are read in place by K2/K3 instead of being copied: same records."""
+    cfg = synth.CONFIGS["cfg2"]
+    B = 5
+    batch = synth.make_batch(cfg, B, seed0=2000)
+    eng = make_engine(cfg, B)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    keep = [pin(batch["frames"])] + [pin(l) for l in batch["levels"]] + [pin(batch["coef"]), pin(batch["proto"])]
+    d1, c1, r1 = eng.process_host(*[t.numpy() for t in keep])                      # pinned: zero copy for p3/p4/p5/coef
+    d2, c2, r2 = eng.process_host(batch["frames"], *batch["levels"], batch["coef"], batch["proto"])   # pageable: copies
+    assert np.array_equal(c1, c2) and r1.tobytes() == r2.tobytes()
+    for b in range(B):
+        assert d1[b, :c1[b]].tobytes() == d2[b, :c2[b]].tobytes()
+
+
 def test_errors_are_reported_not_raised_into_cuda():
     cfg = synth.CONFIGS["cfg2"]
     eng = make_engine(cfg, 1)

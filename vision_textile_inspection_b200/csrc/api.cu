@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "vti_internal.h"
@@ -418,21 +419,44 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     size_t lsz[3];
     for (int l = 0; l < 3; ++l) lsz[l] = (size_t)(64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l];
     const size_t csz = (size_t)VTI_NM * g.A, psz = (size_t)VTI_NM * g.ph * g.pw;
+    // Head tensors that sit in PINNED (device-mapped) host memory are not copied: K2 reads only the class planes and the
+    // 64 box logits of each candidate, K3 only the coefficient rows of the kept detections -- a few hundred KB of the
+    // 4.2 MB per frame -- so those kernels read them in place over PCIe (zero copy) and the DMA engine moves only the
+    // frames and the prototypes.  Pageable buffers are copied as before.
+    const float* dev_p[3];
+    bool zc_p[3];
+    for (int l = 0; l < 3; ++l) {
+        cudaPointerAttributes at;
+        zc_p[l] = !getenv("VTI_NO_ZERO_COPY") && cudaPointerGetAttributes(&at, hp[l]) == cudaSuccess &&
+                  at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+        dev_p[l] = zc_p[l] ? static_cast<const float*>(at.devicePointer) : h->d_p[l];
+    }
+    const float* dev_coef = h->d_coef;
+    bool zc_coef = false;
+    {
+        cudaPointerAttributes at;
+        zc_coef = !getenv("VTI_NO_ZERO_COPY") && cudaPointerGetAttributes(&at, coef) == cudaSuccess &&
+                  at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+        if (zc_coef) dev_coef = static_cast<const float*>(at.devicePointer);
+    }
+    cudaGetLastError();                                    // (a pageable pointer makes the query return an error on old drivers)
     for (int c = 0; c < nchunk; ++c) {
         const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk), nb = b1 - b0;
         if (nb <= 0) continue;
         VTI_CUDA(cudaMemcpyAsync(h->d_frames + b0 * fsz, frames + b0 * fsz, nb * fsz, cudaMemcpyHostToDevice, cs));
         for (int l = 0; l < 3; ++l)
-            VTI_CUDA(cudaMemcpyAsync(h->d_p[l] + b0 * lsz[l], hp[l] + b0 * lsz[l], sizeof(float) * nb * lsz[l],
-                                     cudaMemcpyHostToDevice, cs));
-        VTI_CUDA(cudaMemcpyAsync(h->d_coef + b0 * csz, coef + b0 * csz, sizeof(float) * nb * csz, cudaMemcpyHostToDevice, cs));
+            if (!zc_p[l])
+                VTI_CUDA(cudaMemcpyAsync(h->d_p[l] + b0 * lsz[l], hp[l] + b0 * lsz[l], sizeof(float) * nb * lsz[l],
+                                         cudaMemcpyHostToDevice, cs));
+        if (!zc_coef)
+            VTI_CUDA(cudaMemcpyAsync(h->d_coef + b0 * csz, coef + b0 * csz, sizeof(float) * nb * csz, cudaMemcpyHostToDevice, cs));
         VTI_CUDA(cudaMemcpyAsync(h->d_proto + b0 * psz, proto + b0 * psz, sizeof(float) * nb * psz, cudaMemcpyHostToDevice, cs));
         VTI_CUDA(cudaEventRecord(h->chunk_ev[c], cs));
         VTI_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
         vti_det* cd = h->d_dets + (size_t)b0 * h->p.max_det;
         if ((rc = vti_launch_k1(h, h->d_frames + b0 * fsz, nb, h->d_net_in + b0 * nsz, s))) return rc;
-        if ((rc = vti_launch_k2(h, h->d_p[0] + b0 * lsz[0], h->d_p[1] + b0 * lsz[1], h->d_p[2] + b0 * lsz[2], nb, s))) return rc;
-        if ((rc = vti_launch_k3(h, h->d_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
+        if ((rc = vti_launch_k2(h, dev_p[0] + b0 * lsz[0], dev_p[1] + b0 * lsz[1], dev_p[2] + b0 * lsz[2], nb, s))) return rc;
+        if ((rc = vti_launch_k3(h, dev_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
         if ((rc = vti_launch_k4(h, h->d_proto + b0 * psz, nb, cd, h->d_counts + b0, nullptr, s))) return rc;
         if ((rc = vti_launch_k5(h, nb, cd, h->d_counts + b0, h->d_results + b0, s))) return rc;
         if (net_in)
