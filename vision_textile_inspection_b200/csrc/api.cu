@@ -171,7 +171,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
-                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units};
+                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units, h->d_proto_bbox};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -276,6 +276,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     alloc((void**)&h->d_flags, sizeof(int32_t) * B);
     h->units_per_det = ((g.ph + 1 + VTI_K4_UR - 1) / VTI_K4_UR) * ((g.pw + 1 + VTI_K4_UC - 1) / VTI_K4_UC);
     alloc((void**)&h->d_units, sizeof(uint4) * B * p->max_det * h->units_per_det);
+    alloc((void**)&h->d_proto_bbox, sizeof(int4) * B);
     if (e != cudaSuccess) {
         vti_set_error(std::string("vti_create: cudaMalloc: ") + cudaGetErrorString(e));
         vti_destroy(h);
@@ -439,6 +440,15 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
                   at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
         if (zc_coef) dev_coef = static_cast<const float*>(at.devicePointer);
     }
+    // Pinned prototypes are not DMA-copied either: after K3 a fetch kernel reads, per frame, only the union rectangle of
+    // the crop windows (all that K4 ever touches) over PCIe into the device buffer.
+    const float* map_proto = nullptr;
+    {
+        cudaPointerAttributes at;
+        if (!getenv("VTI_NO_ZERO_COPY") && cudaPointerGetAttributes(&at, proto) == cudaSuccess &&
+            at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+            map_proto = static_cast<const float*>(at.devicePointer);
+    }
     cudaGetLastError();                                    // (a pageable pointer makes the query return an error on old drivers)
     for (int c = 0; c < nchunk; ++c) {
         const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk), nb = b1 - b0;
@@ -450,13 +460,15 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
                                          cudaMemcpyHostToDevice, cs));
         if (!zc_coef)
             VTI_CUDA(cudaMemcpyAsync(h->d_coef + b0 * csz, coef + b0 * csz, sizeof(float) * nb * csz, cudaMemcpyHostToDevice, cs));
-        VTI_CUDA(cudaMemcpyAsync(h->d_proto + b0 * psz, proto + b0 * psz, sizeof(float) * nb * psz, cudaMemcpyHostToDevice, cs));
+        if (!map_proto)
+            VTI_CUDA(cudaMemcpyAsync(h->d_proto + b0 * psz, proto + b0 * psz, sizeof(float) * nb * psz, cudaMemcpyHostToDevice, cs));
         VTI_CUDA(cudaEventRecord(h->chunk_ev[c], cs));
         VTI_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
         vti_det* cd = h->d_dets + (size_t)b0 * h->p.max_det;
         if ((rc = vti_launch_k1(h, h->d_frames + b0 * fsz, nb, h->d_net_in + b0 * nsz, s))) return rc;
         if ((rc = vti_launch_k2(h, dev_p[0] + b0 * lsz[0], dev_p[1] + b0 * lsz[1], dev_p[2] + b0 * lsz[2], nb, s))) return rc;
         if ((rc = vti_launch_k3(h, dev_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
+        if (map_proto && (rc = vti_launch_fetch_proto(h, map_proto + b0 * psz, h->d_proto + b0 * psz, nb, s))) return rc;
         if ((rc = vti_launch_k4(h, h->d_proto + b0 * psz, nb, cd, h->d_counts + b0, nullptr, s))) return rc;
         if ((rc = vti_launch_k5(h, nb, cd, h->d_counts + b0, h->d_results + b0, s))) return rc;
         if (net_in)

@@ -54,6 +54,7 @@ struct K3Args {
     int ph, pw, all_dets, units_per_det;
     int32_t* unit_count;        // one counter for the whole batch
     uint4* units;
+    int4* proto_bbox;           // [B] union of the crop windows K4 will read (x_lo, y_lo, x_hi, y_hi), empty = (1, 1, 0, 0)
 };
 
 // torchvision's test is `float32(inter / uni) > iou` with iou a double.  Let T be the smallest float32 above iou and
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
     __shared__ int s_nk, s_m, s_lo_bin;
     __shared__ int s_upre[MAX_DET_CAP + 1];     // exclusive prefix of K4 work units per kept detection
     __shared__ int s_ubase;
+    __shared__ int s_bb[4];
     __shared__ int s_hist[HIST_BINS];           // candidates per score bin (lazy bucket sort)
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -364,8 +366,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         const int excl = incl - nu + (warp ? s_wsum[warp - 1] : 0);
         if (tid <= nk) s_upre[tid] = excl;                 // s_upre[nk] = total (nu = 0 there)
         const int total = s_wsum[31];
-        if (tid == 0) s_ubase = total ? atomicAdd(a.unit_count, total) : 0;
+        if (tid == 0) { s_ubase = total ? atomicAdd(a.unit_count, total) : 0; s_bb[0] = INT_MAX; s_bb[1] = INT_MAX; s_bb[2] = -1; s_bb[3] = -1; }
         __syncthreads();
+        if (tid < nk && nu > 0) {                          // union of the windows that have work units
+            const int4 w = s_win[tid];
+            atomicMin(&s_bb[0], w.x); atomicMin(&s_bb[1], w.z); atomicMax(&s_bb[2], w.y); atomicMax(&s_bb[3], w.w);
+        }
+        __syncthreads();
+        if (tid == 0) a.proto_bbox[b] = s_bb[2] >= 0 ? make_int4(s_bb[0], s_bb[1], s_bb[2], s_bb[3]) : make_int4(1, 1, 0, 0);
         uint4* __restrict__ units = a.units + s_ubase;
         for (int i = tid; i < total; i += K3_THREADS) {
             int lo = 0, hi = nk - 1;                       // last detection with s_upre[k] <= i
@@ -465,6 +473,7 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
     a.ph = h->g.ph; a.pw = h->g.pw; a.all_dets = all_dets; a.units_per_det = h->units_per_det;
     a.unit_count = h->d_cand_count + h->p.max_batch;
     a.units = h->d_units;
+    a.proto_bbox = h->d_proto_bbox;
     k3_nms_kernel<<<B, K3_THREADS, vti_k3_smem_bytes(h->g.max_candidates), s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());

@@ -355,6 +355,26 @@ __global__ void __launch_bounds__(T_WARPS * 32, 2) k4_tma_kernel(const __grid_co
     }
 }
 
+
+// Host-buffer path: copy, per frame and channel, the union rectangle of the crop windows (the only prototype values the
+// unit kernel reads) from device-mapped pinned host memory into the device prototype buffer.  Rows are widened to
+// 16-byte boundaries for float4 accesses; blockIdx = (channel, frame), warps take rows.
+__global__ void __launch_bounds__(256) k4_fetch_proto_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             const int4* __restrict__ bbox, int ph, int pw) {
+    const int q = blockIdx.x, b = blockIdx.y;
+    const int4 bb = bbox[b];
+    if (bb.z < bb.x || bb.w < bb.y) return;
+    const int x0 = bb.x & ~3, x1 = min((bb.z + 4) & ~3, pw);               // [x0, x1) float4-aligned (pw % 4 == 0)
+    const int n4 = (x1 - x0) >> 2;
+    const size_t plane = (size_t)ph * pw, base = ((size_t)b * VTI_NM + q) * plane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int y = bb.y + warp; y <= bb.w; y += 8) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + base + (size_t)y * pw + x0);
+        float4* d4 = reinterpret_cast<float4*>(dst + base + (size_t)y * pw + x0);
+        for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+    }
+}
+
 }  // namespace
 
 typedef CUresult (*vti_encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -421,6 +441,18 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
         if (masks) k4_units_kernel<true><<<grid, K4_THREADS, 0, s>>>(a);
         else k4_units_kernel<false><<<grid, K4_THREADS, 0, s>>>(a);
     }
+    h->launches++;
+    VTI_CUDA(cudaGetLastError());
+    return VTI_OK;
+}
+
+int vti_launch_fetch_proto(vti_handle* h, const float* host_proto_mapped, float* dev_proto, int B, cudaStream_t s) {
+    if (h->g.pw % 4) {                                     // unaligned rows: plain copy of everything
+        VTI_CUDA(cudaMemcpyAsync(dev_proto, host_proto_mapped, sizeof(float) * (size_t)B * VTI_NM * h->g.ph * h->g.pw,
+                                 cudaMemcpyDefault, s));
+        return VTI_OK;
+    }
+    k4_fetch_proto_kernel<<<dim3(VTI_NM, B), 256, 0, s>>>(host_proto_mapped, dev_proto, h->d_proto_bbox, h->g.ph, h->g.pw);
     h->launches++;
     VTI_CUDA(cudaGetLastError());
     return VTI_OK;

@@ -60,6 +60,7 @@ struct vti_handle {
     uint4* d_units;                                // K4 work units: (frame | fabric << 15 | det << 16, block row | block col << 16,
                                                    //                 cx_lo | cy_lo << 16, cx_hi | cy_hi << 16)
     int units_per_det;                             // capacity per detection slot
+    int4* d_proto_bbox;                            // [B] union of the crop windows of a frame (prototype pixels K4 reads)
     // ---- host-buffer path
     cudaStream_t own_stream, copy_stream;
     cudaEvent_t chunk_ev[4];
@@ -92,6 +93,8 @@ int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_
 int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const int32_t* counts, uint32_t* masks,
                   cudaStream_t s);
 int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* res, cudaStream_t s);
+// copies, per frame, the prototype rectangle K4 will read (all 32 channels) from device-mapped host memory
+int vti_launch_fetch_proto(vti_handle* h, const float* host_proto_mapped, float* dev_proto, int B, cudaStream_t s);
 
 #ifdef __CUDACC__
 // Where a detection's mask can be non-zero.  crop_mask keeps prototype pixel (Y, X) iff X >= x1/4 && X < x2/4 &&
