@@ -161,8 +161,12 @@ int vti_post_measure(vti_handle* h, const float* p3, const float* p4, const floa
                      const float* proto, int B, vti_det* dets, int32_t* counts, uint32_t* masks,
                      vti_frame_result* results, void* stream);
 
-/* End-to-end with HOST buffers (pinned or pageable): H2D of frames + head tensors, K1..K5, D2H of net_in (optional,
- * may be NULL), records, counts and frame results; returns after everything has landed. */
+/* End-to-end with HOST buffers: K1..K5 over the batch in up to 4 pipelined chunks (copies of chunk i+1 under the
+ * kernels of chunk i), D2H of net_in (optional, may be NULL), records, counts and frame results; returns after
+ * everything has landed.  Pageable buffers are copied whole.  PINNED (device-mapped) head tensors are NOT copied:
+ * K2 reads the class planes and the 64 box logits of each candidate in place over PCIe, K3 the coefficient rows of
+ * the kept detections, and a fetch kernel brings only the union rectangle of the crop windows of the prototypes --
+ * the path moves what it reads (the frames always travel by DMA). */
 int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, const float* p4, const float* p5,
                      const float* coef, const float* proto, int B, float* net_in, vti_det* dets, int32_t* counts,
                      vti_frame_result* results);
