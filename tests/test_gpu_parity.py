@@ -452,3 +452,14 @@ def test_k4_tma_form_matches_ldg_form(monkeypatch):
         assert torch.equal(m1[b, :n], m2[b, :n])                   # (slots past the count are never written)
         assert d1[b, :n].tobytes() == d2[b, :n].tobytes()
     assert r1.tobytes() == r2.tobytes()
+
+
+def test_misaligned_frames_are_refused_not_faulted():
+    cfg = synth.CONFIGS["cfg2"]
+    eng = make_engine(cfg, 1)
+    raw = torch.zeros((cfg.frame_h * cfg.frame_w * 3 + 16,), dtype=torch.uint8, device="cuda")
+    out = torch.empty((1, 3, eng.LH, eng.LW), dtype=torch.float32, device="cuda")
+    rc = eng.lib.vti_preprocess(eng._h, raw.data_ptr() + 3, 1, out.data_ptr(), None)       # odd address
+    assert rc == -1 and b"aligned" in eng.lib.vti_last_error()
+    torch.cuda.synchronize()                                                                # no sticky CUDA error
+    assert eng.preprocess(raw[:cfg.frame_h * cfg.frame_w * 3].view(1, cfg.frame_h, cfg.frame_w, 3)).shape[0] == 1

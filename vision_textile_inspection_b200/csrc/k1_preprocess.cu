@@ -732,6 +732,10 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
 
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s) {
     if (h->k1_mode == MODE_FAST_PLAIN || h->k1_mode == MODE_FAST_REMAP) {
+        if ((reinterpret_cast<uintptr_t>(frames) & 7) || (reinterpret_cast<uintptr_t>(net_in) & 3)) {
+            vti_set_error("vti_preprocess: frames must be 8-byte aligned and net_in 4-byte aligned (64-bit staging loads)");
+            return VTI_EINVAL;
+        }
         K1FastArgs f;
         f.frames = frames; f.out = net_in;
         f.tile_hdr = h->d_k1_tiles; f.lut = h->d_k1_lut;
