@@ -349,6 +349,13 @@ extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, 
         vti_set_error("vti_postprocess: null buffer");
         return VTI_EINVAL;
     }
+    if ((reinterpret_cast<uintptr_t>(dets) & 7) || (reinterpret_cast<uintptr_t>(counts) & 3) ||
+        ((reinterpret_cast<uintptr_t>(p3) | reinterpret_cast<uintptr_t>(p4) | reinterpret_cast<uintptr_t>(p5) |
+          reinterpret_cast<uintptr_t>(coef) | reinterpret_cast<uintptr_t>(proto)) & 3) ||
+        (masks && (reinterpret_cast<uintptr_t>(masks) & 15))) {
+        vti_set_error("vti_postprocess: misaligned buffer (dets 8, counts/head tensors 4, masks 16 bytes)");
+        return VTI_EINVAL;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     mark(h, 2, s);
     if ((rc = vti_launch_k2(h, p3, p4, p5, B, s))) return rc;
@@ -365,6 +372,11 @@ extern "C" int vti_measure(vti_handle* h, int B, vti_det* dets, const int32_t* c
     int rc = check_batch(h, B);
     if (rc) return rc;
     if (!dets || !counts || !results) { vti_set_error("vti_measure: null buffer"); return VTI_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(dets) & 7) || (reinterpret_cast<uintptr_t>(results) & 7) ||
+        (reinterpret_cast<uintptr_t>(counts) & 3)) {
+        vti_set_error("vti_measure: misaligned buffer (dets/results 8, counts 4 bytes)");
+        return VTI_EINVAL;
+    }
     mark(h, 6, (cudaStream_t)stream);
     rc = vti_launch_k5(h, B, dets, counts, results, (cudaStream_t)stream);
     mark(h, 7, (cudaStream_t)stream);
