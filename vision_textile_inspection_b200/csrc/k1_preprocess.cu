@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
             const unsigned bw4 = (unsigned)h0.z * 4u;
             const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
             unsigned* dst = s_und + tid;
-            const int n_it = (nrows * a.pitch_u + FT_CHUNK - 1) / FT_CHUNK;     // table and buffer are padded
+            const int total = nrows * a.pitch_u;
+            const int n_it = total / FT_CHUNK;                 // whole chunks; table and buffer are padded
             unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
             for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
                 lut += FT_CHUNK;                               // next entries in flight while these are computed
@@ -474,6 +475,10 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
                 dst[FT_THREADS] = remap_fast(raw, e1, bw4);
                 e0 = n0; e1 = n1;
             }
+            // tail of the footprint: only the warps that still have cells (a 44 x 87 footprint leaves 244 of 512)
+            const int rem = total - n_it * FT_CHUNK;
+            if (tid < rem) dst[0] = remap_fast(raw, e0, bw4);
+            if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast(raw, e1, bw4);
         }
     }
     __syncthreads();
