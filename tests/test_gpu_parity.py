@@ -464,3 +464,32 @@ def test_misaligned_frames_are_refused_not_faulted():
     assert rc == -1 and b"aligned" in eng.lib.vti_last_error()
     torch.cuda.synchronize()                                                                # no sticky CUDA error
     assert eng.preprocess(raw[:cfg.frame_h * cfg.frame_w * 3].view(1, cfg.frame_h, cfg.frame_w, 3)).shape[0] == 1
+
+
+@pytest.mark.parametrize("name,first,count", [("cfg2", 2100, 24), ("cfg3", 3100, 16), ("native", 100, 8)])
+def test_seed_sweep_keep_indices_and_mm(name, first, count, calib):
+    """A wider sweep of planted scenes than POST_CASES: keep indices / counts / boxes bit-exact against the float32
+    spec for every seed, and the fused (no mask export) measurements within 0.1 % of the oracle path for a few."""
+    cfg = synth.CONFIGS[name]
+    seeds = list(range(first, first + count))
+    eng, heads, dets, counts, results, _ = run_gpu(cfg, seeds, export_masks=False)
+    for b, hd in enumerate(heads):
+        sp = post_spec.postprocess_spec(hd["levels"], hd["coef"], cfg.conf, cfg.iou, cfg.max_det, cfg.nc, cfg.LH,
+                                        cfg.LW, cfg.frame_h, cfg.frame_w)
+        n = int(counts[b])
+        assert n == len(sp["keep_anchor"]), (seeds[b], n)
+        d = dets[b, :n]
+        assert np.array_equal(d["anchor"], sp["keep_anchor"]), seeds[b]
+        assert np.array_equal(d["conf"].view(np.uint32), sp["conf"].view(np.uint32))
+        assert np.array_equal(d["box_lb"].view(np.uint32), sp["box_lb"].view(np.uint32))
+    for b in range(0, count, max(count // 4, 1)):
+        _, _, m = helpers.oracle_scene(cfg, seeds[b], calib)
+        r = results[b]
+        assert r["status"] == {"ok": 0, "no_fabric": 2, "no_stitch": 3}[m["status"]], seeds[b]
+        if m["status"] == "ok":
+            assert r["n_dist"] == m["n_dist"] and r["n_width"] == m["n_width"]
+            for key, ref in (("avg_dist", m["avg_dist"]), ("avg_width", m["avg_width"])):
+                if ref is None:
+                    assert np.isnan(r[key])
+                else:
+                    assert abs(r[key] - ref) <= MM_RTOL * ref, (seeds[b], key, r[key], ref)
