@@ -255,6 +255,20 @@ def run_b200(args, cfg, rank, world, local_rank):
     bufs = [shard.alloc_packed(B, cfg.max_det, dev) for _ in range(2)]
     packed, outs = bufs[0]
     gathered = [torch.empty((world * bufs[0][0].numel(),), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    # Records travel to rank 0 through NVLink peer memory (shard.PeerGather: one copy-engine copy + a signal per rank
+    # and step, no collective kernel); an NCCL all-gather of the same buffers is the fallback when symmetric memory
+    # cannot be set up on this box, and what --gather nccl selects.
+    peer = None
+    if world > 1 and args.gather == "peer":
+        try:
+            peer = shard.PeerGather(bufs[0][0].numel(), dev)
+        except Exception as e:                                   # noqa: BLE001  (said out loud, then NCCL)
+            print(f"[bench] rank {rank}: peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather",
+                  file=sys.stderr)
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # all ranks or none
+        if int(flag.item()) == 0:
+            peer = None
     in_bytes = (d_frames.numel() + 4 * (sum(l.numel() for l in d_lv) + d_coef.numel() + d_proto.numel()))
     out_bytes = 4 * net_in.numel()
 
@@ -285,7 +299,10 @@ def run_b200(args, cfg, rank, world, local_rank):
         if world > 1:
             s_gather.wait_stream(s_post)
             with torch.cuda.stream(s_gather):
-                dist.all_gather_into_tensor(gathered[k], pk)   # ranks in frame order; shard.unpack_packed gives the views
+                if peer is not None:
+                    peer.push(pk, k)                           # rank 0 reads peer.gathered(k)
+                else:
+                    dist.all_gather_into_tensor(gathered[k], pk)   # ranks in frame order; shard.unpack_packed gives the views
                 ev_gather[k] = torch.cuda.Event()
                 ev_gather[k].record(s_gather)
         with torch.cuda.stream(s_pre):
@@ -343,6 +360,21 @@ def run_b200(args, cfg, rank, world, local_rank):
         ms = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
+    gather_checked = None
+    if world > 1:
+        # what reached rank 0 must be every rank's own records (checked on the per-frame counts and result bytes)
+        k_last = (state["i"] - 1) & 1
+        mine = torch.cat([bufs[k_last][1][1].view(torch.uint8).view(-1), bufs[k_last][1][2].reshape(-1)])
+        ref_all = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(ref_all.view(-1), mine)
+        if rank == 0:
+            got = peer.gathered(k_last) if peer is not None else gathered[k_last].view(world, -1)
+            _, g_counts, g_results = shard.unpack_packed(got, B, cfg.max_det)
+            got_cat = torch.cat([g_counts.view(world, -1).view(torch.uint8).view(world, -1),
+                                 g_results.reshape(world, -1)], dim=1)
+            gather_checked = bool(torch.equal(got_cat, ref_all))
+            if not gather_checked:
+                raise RuntimeError("record gather: rank 0 did not receive every rank's records")
 
     # ---- per-kernel durations (CUDA events recorded by the library on the launching stream), same inputs
     eng.set_profiling(True)
@@ -473,7 +505,11 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "net_in": [cfg.LW, cfg.LH], "anchors": cfg.anchors, "undistort": cfg.undistort,
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                   "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority) + the record all-gather on a third (double-buffered records), joined at the ends of the timed region",
+                   "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority) + the record gather on a third (double-buffered records), joined at the ends of the timed region",
+                   "gather": ("none (1 GPU)" if world == 1 else
+                              "peer memory: per rank and step one copy-engine copy of the packed records into rank 0's symmetric buffer + signal, no collective kernel"
+                              if peer is not None else "NCCL all-gather of the packed records"),
+                   "gather_checked": gather_checked,
                    "clock_sampling": "nvidia-smi every 100 ms over the timed steps + an untimed continuation of the same loop",
                    "status_ok_frames": int((res["status"] == 0).sum())},
         "clocks": clocks,
@@ -514,6 +550,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: records to rank 0 through NVLink peer memory (default) or an NCCL all-gather")
     args = ap.parse_args()
     _protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -493,3 +493,28 @@ def test_seed_sweep_keep_indices_and_mm(name, first, count, calib):
                     assert np.isnan(r[key])
                 else:
                     assert abs(r[key] - ref) <= MM_RTOL * ref, (seeds[b], key, r[key], ref)
+
+
+def test_peer_gather_single_rank_roundtrip():
+    """shard.PeerGather (the NVLink peer-memory gather-to-root of bench.py --gpus N) wired through a 1-rank NCCL group:
+    what is pushed into a slot is what root reads back, slot by slot, and unpack_packed() returns the typed views."""
+    import torch.distributed as dist
+    from vision_textile_inspection_b200 import shard
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    try:
+        B, max_det = 4, 16
+        packed, (dets, counts, results, _) = shard.alloc_packed(B, max_det, torch.device("cuda", 0))
+        pg = shard.PeerGather(packed.numel(), torch.device("cuda", 0))
+        for step in range(4):
+            packed.copy_(torch.randint(0, 256, (packed.numel(),), dtype=torch.uint8, device="cuda"))
+            pg.push(packed, step & 1)
+            torch.cuda.synchronize()
+            got = pg.gathered(step & 1)
+            assert got.shape == (1, packed.numel()) and torch.equal(got[0], packed)
+            d, c, r = shard.unpack_packed(got, B, max_det)
+            assert torch.equal(d.reshape(-1), dets.reshape(-1)) and torch.equal(c, counts) and torch.equal(r, results)
+    finally:
+        if created:
+            dist.destroy_process_group()

@@ -56,3 +56,41 @@ def unpack_packed(gathered: torch.Tensor, B: int, max_det: int):
     results = gathered[:, nd:nd + nr].reshape(W * B, RESULT_DTYPE.itemsize)
     counts = gathered[:, nd + nr:].contiguous().view(torch.int32).reshape(W * B)
     return dets, counts, results
+
+
+class PeerGather:
+    """Gather-to-root of the packed per-rank records over NVLink peer memory, with no collective kernel on any SM.
+
+    SURVEY.md 8e asks for the records on rank 0 (the host logic of main.py:225-293 runs once, in frame order), so an
+    all-gather moves W times more bytes than needed and its NCCL kernel takes SMs from K1.  Here every rank owns a
+    symmetric-memory buffer [slots][W][bytes]; a rank pushes its packed records into ROOT's copy of slot s, row
+    `rank`, with one device-to-device copy through the peer mapping (copy engine over NVLink / NVSwitch), then raises
+    a signal that root's stream waits on.  The signal handshake is also the flow control: a rank cannot raise signal
+    s + 1 before root has consumed signal s, so with two slots a row is never overwritten while root may still read it.
+    """
+
+    def __init__(self, nbytes: int, device, group=None, root: int = 0, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world, self.root, self.slots = dist.get_rank(group), dist.get_world_size(group), root, slots
+        self.nbytes = nbytes
+        self.buf = symm.empty((slots, self.world, nbytes), dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.root_buf = self.hdl.get_buffer(root, (slots, self.world, nbytes), torch.uint8)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()
+
+    def push(self, packed: torch.Tensor, slot: int) -> None:
+        """Enqueue, on the current stream, this rank's copy into root's slot and the signal exchange."""
+        self.root_buf[slot, self.rank].copy_(packed.view(-1))
+        if self.rank != self.root:
+            self.hdl.put_signal(self.root, channel=self.rank)
+        else:
+            for r in range(self.world):
+                if r != self.root:
+                    self.hdl.wait_signal(r, channel=r)
+
+    def gathered(self, slot: int) -> torch.Tensor:
+        """Root only: (W, bytes) view of a slot; unpack_packed() gives the typed views in global frame order."""
+        return self.buf[slot]
