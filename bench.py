@@ -6,7 +6,8 @@
 A step = one pass of the hot path (K1 undistort+letterbox, K2 decode/filter, K3 NMS, K4 masks+statistics, K5 measure)
 over one batch of synthetic frames + planted head tensors already resident in HBM.  N=1 workload = BASELINE.json
 configs[1] (64 x 1280x720, undistort on).  For N>1 the driver launches one rank per GPU with torchrun; every rank runs
-its own batch (weak scaling, no data-path collective) and the compact per-defect records are all-gathered each step.
+its own batch (weak scaling, no data-path collective) and pushes its compact per-defect records to rank 0 each step
+through NVLink peer memory (shard.PeerGather; --gather nccl = an all-gather of the same buffers).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
