@@ -71,18 +71,24 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
     long long m00 = 0, m10 = 0, m01 = 0;
     int cmin = INT_MAX, cmax = -1;
     uint32_t* __restrict__ mrow = EXPORT ? a.masks + ((size_t)b * a.max_det + k) * a.LH * (a.LW / 32) : nullptr;
-    for (int i = lane; i < (nr - 1) * ncc; i += 32) {
+    const int ncells = (nr - 1) * ncc;
+    for (int i0 = 0; i0 < ncells; i0 += 32) {              // warp-uniform trip count: the boundary cells are shared out below
+        const int i = i0 + lane;
         const int r = (int)(((float)i + 0.5f) * inv_ncc), c = i - r * ncc;
         // cell (R, C) covers output rows 4R-2 .. 4R+1 and cols 4C-2 .. 4C+1, clipped to the image
         const int cy_first = 4 * (R0 + r) - 2, cx_first = 4 * (C0 + c) - 2;
         const int ya = max(cy_first, 0), yb = min(cy_first + 3, a.LH - 1);
         const int xa = max(cx_first, 0), xb = min(cx_first + 3, a.LW - 1);
-        if (ya > yb || xa > xb) continue;
-        const float c00 = sc[r * SCW + c], c01 = sc[r * SCW + c + 1];
-        const float c10 = sc[(r + 1) * SCW + c], c11 = sc[(r + 1) * SCW + c + 1];
+        const bool valid = i < ncells && ya <= yb && xa <= xb;
+        float c00 = 0.0f, c01 = 0.0f, c10 = 0.0f, c11 = 0.0f;
+        if (valid) {
+            c00 = sc[r * SCW + c]; c01 = sc[r * SCW + c + 1];
+            c10 = sc[(r + 1) * SCW + c]; c11 = sc[(r + 1) * SCW + c + 1];
+        }
         const float vmin = fminf(fminf(c00, c01), fminf(c10, c11));
         const float vmax = fmaxf(fmaxf(c00, c01), fmaxf(c10, c11));
-        if (vmin > 0.5f + MARGIN) {
+        const bool full = valid && vmin > 0.5f + MARGIN;
+        if (full) {
             // fully set: closed form from the prefix sums of the nearest-resize multiplicity tables
             const int f_cy = a.ly.pc[yb + 1] - a.ly.pc[ya], f_sy = a.ly.ps[yb + 1] - a.ly.ps[ya];
             const int f_cx = a.lx.pc[xb + 1] - a.lx.pc[xa], f_sx = a.lx.ps[xb + 1] - a.lx.ps[xa];
@@ -106,35 +112,40 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
                     if ((unsigned)(bits >> 32)) atomicOr(wp + 1, (unsigned)(bits >> 32));
                 }
             }
-        } else if (vmax >= 0.5f - MARGIN) {
-            // boundary cell: evaluate its pixels (torch upsample_bilinear2d, align_corners=False, scale 1/4)
-            for (int Y = ya; Y <= yb; ++Y) {
-                const float ly1 = (float)(2 * (Y - cy_first) + 1) * 0.125f;
-                const int cY = a.ly.cnt[Y], sY = a.ly.sum[Y];
-                unsigned long long rowbits = 0ull;
-                for (int X = xa; X <= xb; ++X) {
-                    const float lx1 = (float)(2 * (X - cx_first) + 1) * 0.125f;
-                    const float top = (1.0f - lx1) * c00 + lx1 * c01;
-                    const float bot = (1.0f - lx1) * c10 + lx1 * c11;
-                    const float v = (1.0f - ly1) * top + ly1 * bot;
-                    if (v > 0.5f) {
-                        rowbits |= 1ull << ((X - xa) + (xa & 31));
-                        const int cX = a.lx.cnt[X];
-                        m00 += cY * cX; m10 += cY * a.lx.sum[X]; m01 += sY * cX;
-                        if (cY > 0 && cX > 0) {
-                            cmin = min(cmin, a.lx.first[X]);
-                            cmax = max(cmax, a.lx.last[X]);
-                            if (fabric) {
-                                if (a.upper) atomicMin(&envw[X - ex0], a.ly.first[Y]);
-                                else atomicMax(&envw[X - ex0], a.ly.last[Y]);
-                            }
+        }
+        // Boundary cells evaluate their 16 pixels (torch upsample_bilinear2d, align_corners=False, scale 1/4).  Few lanes
+        // of a warp hold one -- the mask edge crosses a unit as a line -- so the warp takes them two at a time, one
+        // pixel per lane, instead of every holder looping over its 16 pixels with the other lanes idle.
+        unsigned bm = __ballot_sync(0xffffffffu, valid && !full && vmax >= 0.5f - MARGIN);
+        while (bm) {
+            const int s0 = __ffs(bm) - 1;
+            bm &= bm - 1;
+            const bool pair = bm != 0u;
+            const int s1 = pair ? __ffs(bm) - 1 : s0;
+            bm &= bm - 1;
+            const int src = lane < 16 ? s0 : s1;
+            const float q00 = __shfl_sync(0xffffffffu, c00, src), q01 = __shfl_sync(0xffffffffu, c01, src);
+            const float q10 = __shfl_sync(0xffffffffu, c10, src), q11 = __shfl_sync(0xffffffffu, c11, src);
+            const int rc = __shfl_sync(0xffffffffu, (r << 16) | c, src);
+            const int py = (lane >> 2) & 3, px = lane & 3;
+            const int Y = 4 * (R0 + (rc >> 16)) - 2 + py, X = 4 * (C0 + (rc & 0xFFFF)) - 2 + px;
+            if ((lane < 16 || pair) && Y >= 0 && Y < a.LH && X >= 0 && X < a.LW) {
+                const float ly1 = (float)(2 * py + 1) * 0.125f, lx1 = (float)(2 * px + 1) * 0.125f;
+                const float top = (1.0f - lx1) * q00 + lx1 * q01;
+                const float bot = (1.0f - lx1) * q10 + lx1 * q11;
+                const float v = (1.0f - ly1) * top + ly1 * bot;
+                if (v > 0.5f) {
+                    const int cY = a.ly.cnt[Y], sY = a.ly.sum[Y], cX = a.lx.cnt[X];
+                    m00 += cY * cX; m10 += cY * a.lx.sum[X]; m01 += sY * cX;
+                    if (cY > 0 && cX > 0) {
+                        cmin = min(cmin, a.lx.first[X]);
+                        cmax = max(cmax, a.lx.last[X]);
+                        if (fabric) {
+                            if (a.upper) atomicMin(&envw[X - ex0], a.ly.first[Y]);
+                            else atomicMax(&envw[X - ex0], a.ly.last[Y]);
                         }
                     }
-                }
-                if (EXPORT && rowbits) {
-                    uint32_t* wp = mrow + (size_t)Y * (a.LW / 32) + (xa >> 5);
-                    if ((unsigned)rowbits) atomicOr(wp, (unsigned)rowbits);
-                    if ((unsigned)(rowbits >> 32)) atomicOr(wp + 1, (unsigned)(rowbits >> 32));
+                    if (EXPORT) atomicOr(mrow + (size_t)Y * (a.LW / 32) + (X >> 5), 1u << (X & 31));
                 }
             }
         }
