@@ -32,7 +32,10 @@
 
 namespace {
 
-constexpr int K4_THREADS = 256;
+#ifndef VTI_K4_THREADS
+#define VTI_K4_THREADS 256
+#endif
+constexpr int K4_THREADS = VTI_K4_THREADS;
 constexpr int NWARP = K4_THREADS / 32;
 constexpr int UR = VTI_K4_UR, UC = VTI_K4_UC;
 constexpr int SCW = UC + 1;                 // corner columns per unit
@@ -181,7 +184,7 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
 }
 
 template <bool EXPORT>
-__global__ void __launch_bounds__(K4_THREADS, 4) k4_units_kernel(const K4Args a) {
+__global__ void __launch_bounds__(K4_THREADS, 1024 / K4_THREADS) k4_units_kernel(const K4Args a) {
     __shared__ float s_c[NWARP][(UR + 1) * SCW];
     __shared__ __align__(16) float s_coef[NWARP][VTI_NM];   // registers go to the 32 in-flight prototype loads
     __shared__ int s_envw[NWARP][4 * UC];                   // fabric envelope of the unit's columns (one RED each)
@@ -447,8 +450,12 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
         if (masks) k4_tma_kernel<true><<<grid, T_WARPS * 32, K4_TMA_SMEM, s>>>(tmap, a);
         else k4_tma_kernel<false><<<grid, T_WARPS * 32, K4_TMA_SMEM, s>>>(tmap, a);
     } else {
-        // LDG form (no driver entry point, unaligned prototype pointer): four 8-warp CTAs per SM
-        const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : 4) * h->num_sms;
+        // LDG form.  Alone, K4 is fastest with four 8-warp CTAs per SM (66 vs 88 us on cfg2), but those fill every
+        // register file and K1 -- which runs beside it on the pre stream -- then waits for K4 to finish.  Two CTAs per
+        // SM leave half of each SM to K1: the K1 || K2-K5 step is 2.3 % faster on cfg2 / cfg3.  When K1 has little to do
+        // (no remap, no resize: cfg4) K4 is on the critical path and keeps the four.  VTI_K4_GRID overrides.
+        const bool k1_heavy = h->p.undistort || h->p.frame_w != h->g.new_w || h->p.frame_h != h->g.new_h;
+        const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : (k1_heavy ? 2 : 4)) * h->num_sms;
         if (masks) k4_units_kernel<true><<<grid, K4_THREADS, 0, s>>>(a);
         else k4_units_kernel<false><<<grid, K4_THREADS, 0, s>>>(a);
     }
