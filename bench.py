@@ -243,6 +243,11 @@ def run_b200(args, cfg, rank, world, local_rank):
     n_unique = min(B, 8)
     batch = synth.make_batch(cfg, B, seed0=1000 * cfg.cfg_id + 100 * rank, n_unique=n_unique)
     eng = InspectionEngine(EngineConfig.for_workload(cfg, calib, max_batch=B), device=dev)
+    # --post-streams 2: consecutive batches are independent, so their post stages may overlap -- a second handle (its
+    # own candidate lists and unit list) takes the odd steps on a second post stream.  That pays when the
+    # K2 -> K3 -> K4 -> K5 chain, not K1, bounds the step (cfg4: 138 -> 208 k frames/s); cfg2 is K1-bound and keeps one.
+    engs = [eng, InspectionEngine(EngineConfig.for_workload(cfg, calib, max_batch=B), device=dev)] \
+        if args.post_streams == 2 else [eng, eng]
 
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = {k: pin(batch[k]) for k in ("frames", "coef", "proto")}
@@ -276,6 +281,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     # Pre (K1) and post+measure (K2..K5) of one batch are independent -- the backbone sits between them -- so they are
     # issued on two streams: the latency-bound per-frame CTAs of K3/K5 run under the streaming K1.
     s_pre, s_post = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)   # post CTAs win free SM slots
+    s_posts = [s_post, torch.cuda.Stream(dev, priority=-1) if args.post_streams == 2 else s_post]
     s_gather = torch.cuda.Stream(dev, priority=-1)
     ev_gather = [None, None]
     state = {"i": 0}
@@ -293,12 +299,12 @@ def run_b200(args, cfg, rank, world, local_rank):
         k = state["i"] & 1
         state["i"] += 1
         pk, ot = bufs[k]
-        with torch.cuda.stream(s_post):
+        with torch.cuda.stream(s_posts[k]):
             if world > 1 and ev_gather[k] is not None:
-                s_post.wait_event(ev_gather[k])                # buffer k was gathered two steps ago
-            eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=ot)
+                s_posts[k].wait_event(ev_gather[k])            # buffer k was gathered two steps ago
+            engs[k].post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=ot)
         if world > 1:
-            s_gather.wait_stream(s_post)
+            s_gather.wait_stream(s_posts[k])
             with torch.cuda.stream(s_gather):
                 if peer is not None:
                     peer.push(pk, k)                           # rank 0 reads peer.gathered(k)
@@ -312,13 +318,15 @@ def run_b200(args, cfg, rank, world, local_rank):
     def fork():
         cur = torch.cuda.current_stream(dev)
         s_pre.wait_stream(cur)
-        s_post.wait_stream(cur)
+        for sp in s_posts:
+            sp.wait_stream(cur)
         s_gather.wait_stream(cur)
 
     def join():
         cur = torch.cuda.current_stream(dev)
         cur.wait_stream(s_pre)
-        cur.wait_stream(s_post)
+        for sp in s_posts:
+            cur.wait_stream(sp)
         cur.wait_stream(s_gather)
 
     def barrier():
@@ -335,7 +343,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    l0 = eng.launch_count
+    l0 = sum(e.launch_count for e in set(engs))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -345,7 +353,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         step()
     join()
     e1.record()
-    launches = eng.launch_count - l0
+    launches = sum(e.launch_count for e in set(engs)) - l0
     # The timed region is K steps (a few ms); nvidia-smi samples every 100 ms.  The identical loop keeps running,
     # untimed, until >= 0.5 s of load has been sampled, so "clocks" describes this workload under load.
     fork()
@@ -507,6 +515,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
                    "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority) + the record gather on a third (double-buffered records), joined at the ends of the timed region",
+                   "post_streams": args.post_streams,
                    "gather": ("none (1 GPU)" if world == 1 else
                               "peer memory: per rank and step one copy-engine copy of the packed records into rank 0's symmetric buffer + signal, no collective kernel"
                               if peer is not None else "NCCL all-gather of the packed records"),
@@ -551,6 +560,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
+    ap.add_argument("--post-streams", type=int, default=1, choices=[1, 2],
+                    help="2: the post stages of consecutive batches overlap (two handles, two post streams); measured: no "
+                         "gain on cfg2 (K1-bound, 221 vs 226 k frames/s), +50 %% on the post-bound stress config cfg4")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: records to rank 0 through NVLink peer memory (default) or an NCCL all-gather")
     args = ap.parse_args()
