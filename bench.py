@@ -476,6 +476,23 @@ def run_b200(args, cfg, rank, world, local_rank):
     latency = {"ms_median": float(np.median(lat)), "ms_p90": float(np.percentile(lat, 90)), "frames": 1,
                "api": "app.B200Predictor.run, one frame from host memory to host records (H2D + K1..K5 + D2H)"}
 
+    # ---- the same step as ONE CUDA graph (K1 forked beside K2..K5, joined at the end), replayed back to back on one
+    #      stream: one launch per step instead of six, but the join at the end of every graph gives up the overlap
+    #      ACROSS steps that the stream form keeps (informational)
+    graph, _, _ = eng.capture_step(d_frames, d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, net_in=net_in, outputs=outs)
+    for _ in range(3):
+        graph.replay()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    g1.record()
+    torch.cuda.synchronize()
+    graph_ms = g0.elapsed_time(g1) / args.steps
+    graph_step = {"ms_per_step": graph_ms, "frames_per_s": B / (graph_ms * 1e-3),
+                  "api": "engine.capture_step: one CUDA graph per step (K1 || K2-K5), replays serialised on one stream"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -533,6 +550,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                        "(fetch kernel before K4)"},
         "e2e_frames_only": e2e_frames_only,
         "latency_single_frame": latency,
+        "graph_step": graph_step,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * sb[names[dom]]},

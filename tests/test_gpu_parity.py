@@ -518,3 +518,34 @@ def test_peer_gather_single_rank_roundtrip():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_cuda_graph_step_replays_bit_identically():
+    """K1 || K2..K5 captured as one CUDA graph (engine.capture_step): a replay reproduces the eager records byte for
+    byte, and a replay after the input buffers were overwritten in place reflects the new inputs."""
+    cfg = synth.CONFIGS["cfg2"]
+    seeds_a, seeds_b = [2000, 2001], [2002, 2003]
+
+    def inputs(seeds):
+        heads = [synth.planted_head(cfg, s) for s in seeds]
+        frames = np.stack([synth.fabric_frame(cfg, s) for s in seeds])
+        return (dev(frames), *[dev(np.stack([h["levels"][l] for h in heads])) for l in range(3)],
+                dev(np.stack([h["coef"] for h in heads])), dev(np.stack([h["proto"] for h in heads])))
+
+    eng = make_engine(cfg, 2)
+    bufs = inputs(seeds_a)
+    graph, net_in, (dets, counts, results, _) = eng.capture_step(*bufs)
+    for seeds in (seeds_a, seeds_b):
+        fresh = inputs(seeds)
+        for dst, src in zip(bufs, fresh):
+            dst.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (net_in.clone(), dets.clone(), counts.clone(), results.clone())
+        ref_in = eng.preprocess(fresh[0])
+        rd, rc, rr, _ = eng.post_measure(*fresh[1:])
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], ref_in) and torch.equal(got[2], rc) and torch.equal(got[3], rr)
+        for b in range(2):
+            n = int(rc[b])
+            assert n > 0 and torch.equal(got[1][b, :n], rd[b, :n])

@@ -199,6 +199,32 @@ class InspectionEngine:
                                             self._stream()), "vti_post_measure")
         return dets, counts, results, masks
 
+    def capture_step(self, frames, p3, p4, p5, coef, proto, net_in=None, outputs=None, export_masks: bool = False):
+        """One pass of the hot path as ONE CUDA graph: K1 on a forked branch beside K2 -> K3 -> K4 -> K5, joined at the
+        end.  The stage entry points only launch kernels on the stream they are handed (no allocation, no
+        synchronisation), so they are capturable as they are.  Returns (graph, net_in, (dets, counts, results, masks));
+        `graph.replay()` re-runs the step on the CURRENT contents of the captured buffers."""
+        B = self._check_head(p3, p4, p5, coef, proto)
+        self._chk(frames, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "frames")
+        if net_in is None:
+            net_in = torch.empty((B, 3, self.LH, self.LW), dtype=torch.float32, device=self.device)
+        if outputs is None:
+            outputs = self.alloc_outputs(B, export_masks)
+        with torch.cuda.device(self.device):
+            self.preprocess(frames, out=net_in)              # warm-up outside the capture (lazy module loading)
+            self.post_measure(p3, p4, p5, coef, proto, outputs=outputs)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.device, priority=-1)   # kernel nodes keep the priority of their stream:
+            with torch.cuda.graph(graph):                        # the post CTAs win free SM slots over K1's 16 k CTAs
+                cur = torch.cuda.current_stream(self.device)
+                side.wait_stream(cur)                        # fork: K1 does not depend on the post stage
+                with torch.cuda.stream(side):
+                    self.post_measure(p3, p4, p5, coef, proto, outputs=outputs)
+                self.preprocess(frames, out=net_in)
+                cur.wait_stream(side)                        # join
+        return graph, net_in, outputs
+
     def process_host(self, frames: np.ndarray, p3, p4, p5, coef, proto, want_net_in: bool = False, out=None):
         """End-to-end with HOST numpy buffers (ideally pinned): H2D, K1..K5, D2H.  Returns (dets, counts, results[, net_in])."""
         B = frames.shape[0]
