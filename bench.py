@@ -286,7 +286,23 @@ def run_b200(args, cfg, rank, world, local_rank):
     ev_gather = [None, None]
     state = {"i": 0}
 
-    def step(overlap=True):
+    # --step-form graph (default): one step = ONE CUDA graph (engine.capture_step: K1 beside K2..K5 on a forked
+    # high-priority branch, joined at the end), one graph per record buffer, replayed on the current stream.  Measured
+    # 2 % faster than issuing the same six kernels on two streams every step (--step-form streams, below).
+    graphs, nodes_per_graph = None, 0
+    if args.step_form == "graph" and args.post_streams == 1:
+        try:
+            l_b = eng.launch_count
+            graphs = [eng.capture_step(d_frames, d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, net_in=net_in,
+                                       outputs=bufs[k][1])[0] for k in range(2)]
+            nodes_per_graph = (eng.launch_count - l_b) // 4        # per graph: one eager warm-up pass + the capture
+        except Exception as e:                                     # noqa: BLE001  (said out loud, then the stream form)
+            print(f"[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); using the stream form",
+                  file=sys.stderr)
+            graphs = None
+    replays = {"n": 0}
+
+    def step(overlap=True, use_graph=None):
         """One pass of the hot path over one batch.  overlap=True: K1 goes to s_pre, K2..K5 (+ the record gather) to
         s_post and the two streams are NOT joined per step -- consecutive batches are independent, exactly as in a
         pipeline with the backbone between pre and post -- fork()/join() bracket the timed region instead."""
@@ -299,6 +315,22 @@ def run_b200(args, cfg, rank, world, local_rank):
         k = state["i"] & 1
         state["i"] += 1
         pk, ot = bufs[k]
+        if graphs is not None and use_graph is not False:
+            cur = torch.cuda.current_stream(dev)
+            if world > 1 and ev_gather[k] is not None:
+                cur.wait_event(ev_gather[k])                   # buffer k was gathered two steps ago
+            graphs[k].replay()
+            replays["n"] += 1
+            if world > 1:
+                s_gather.wait_stream(cur)
+                with torch.cuda.stream(s_gather):
+                    if peer is not None:
+                        peer.push(pk, k)
+                    else:
+                        dist.all_gather_into_tensor(gathered[k], pk)
+                    ev_gather[k] = torch.cuda.Event()
+                    ev_gather[k].record(s_gather)
+            return
         with torch.cuda.stream(s_posts[k]):
             if world > 1 and ev_gather[k] is not None:
                 s_posts[k].wait_event(ev_gather[k])            # buffer k was gathered two steps ago
@@ -343,7 +375,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    l0 = sum(e.launch_count for e in set(engs))
+    l0 = sum(e.launch_count for e in set(engs)) + nodes_per_graph * replays["n"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -353,7 +385,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         step()
     join()
     e1.record()
-    launches = sum(e.launch_count for e in set(engs)) - l0
+    launches = sum(e.launch_count for e in set(engs)) + nodes_per_graph * replays["n"] - l0   # graph kernel nodes count
     # The timed region is K steps (a few ms); nvidia-smi samples every 100 ms.  The identical loop keeps running,
     # untimed, until >= 0.5 s of load has been sampled, so "clocks" describes this workload under load.
     fork()
@@ -476,22 +508,32 @@ def run_b200(args, cfg, rank, world, local_rank):
     latency = {"ms_median": float(np.median(lat)), "ms_p90": float(np.percentile(lat, 90)), "frames": 1,
                "api": "app.B200Predictor.run, one frame from host memory to host records (H2D + K1..K5 + D2H)"}
 
-    # ---- the same step as ONE CUDA graph (K1 forked beside K2..K5, joined at the end), replayed back to back on one
-    #      stream: one launch per step instead of six, but the join at the end of every graph gives up the overlap
-    #      ACROSS steps that the stream form keeps (informational)
-    graph, _, _ = eng.capture_step(d_frames, d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, net_in=net_in, outputs=outs)
-    for _ in range(3):
-        graph.replay()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    g0.record()
-    for _ in range(args.steps):
-        graph.replay()
-    g1.record()
-    torch.cuda.synchronize()
-    graph_ms = g0.elapsed_time(g1) / args.steps
-    graph_step = {"ms_per_step": graph_ms, "frames_per_s": B / (graph_ms * 1e-3),
-                  "api": "engine.capture_step: one CUDA graph per step (K1 || K2-K5), replays serialised on one stream"}
+    # ---- the OTHER step form, timed the same way (informational): with --step-form graph this is the two-stream form
+    #      (six launches per step, streams joined only at the ends), with --step-form streams the graph form
+    other = None
+    if world == 1 and args.post_streams == 1:
+        if graphs is not None:
+            def other_step():
+                step(use_graph=False)
+            name = "streams"
+        else:
+            g_alt = eng.capture_step(d_frames, d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, net_in=net_in, outputs=outs)[0]
+            other_step, name = g_alt.replay, "graph"
+        fork()
+        for _ in range(3):
+            other_step()
+        join()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        fork()
+        for _ in range(args.steps):
+            other_step()
+        join()
+        g1.record()
+        torch.cuda.synchronize()
+        o_ms = g0.elapsed_time(g1) / args.steps
+        other = {"step_form": name, "ms_per_step": o_ms, "frames_per_s": B / (o_ms * 1e-3)}
 
     if rank != 0:
         if world > 1:
@@ -531,7 +573,10 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "net_in": [cfg.LW, cfg.LH], "anchors": cfg.anchors, "undistort": cfg.undistort,
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                   "unique_frames": n_unique, "streams": "K1 || K2-K5 on two streams (post at high priority) + the record gather on a third (double-buffered records), joined at the ends of the timed region",
+                   "unique_frames": n_unique, "streams": ("one CUDA graph per step: K1 beside K2-K5 on a forked high-priority branch, joined at the end of the graph; the record gather on its own stream (double-buffered records)"
+                               if graphs is not None else
+                               "K1 || K2-K5 on two streams (post at high priority) + the record gather on a third (double-buffered records), joined at the ends of the timed region"),
+                   "step_form": "graph" if graphs is not None else "streams",
                    "post_streams": args.post_streams,
                    "gather": ("none (1 GPU)" if world == 1 else
                               "peer memory: per rank and step one copy-engine copy of the packed records into rank 0's symmetric buffer + signal, no collective kernel"
@@ -550,7 +595,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                        "(fetch kernel before K4)"},
         "e2e_frames_only": e2e_frames_only,
         "latency_single_frame": latency,
-        "graph_step": graph_step,
+        "other_step_form": other,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * sb[names[dom]]},
@@ -578,6 +623,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
+    ap.add_argument("--step-form", default="graph", choices=["graph", "streams"],
+                    help="graph: one CUDA graph replay per step; streams: the six kernels issued on two streams per step")
     ap.add_argument("--post-streams", type=int, default=1, choices=[1, 2],
                     help="2: the post stages of consecutive batches overlap (two handles, two post streams); measured: no "
                          "gain on cfg2 (K1-bound, 221 vs 226 k frames/s), +50 %% on the post-bound stress config cfg4")

@@ -206,6 +206,16 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     h->p = *p;
     int rc = vti_plan_geometry(p->frame_h, p->frame_w, p->imgsz, p->stride, p->max_det, p->max_candidates, &h->g);
     if (rc) { delete h; return rc; }
+    {
+        // K4 accumulates a work unit's moments (<= 1024 letterbox pixels, each standing for up to my x mx frame pixels
+        // at coordinates < max(h, w)) in 32 bits before its 64-bit atomics
+        const unsigned long long my = (p->frame_h + h->g.LH - 1) / h->g.LH + 1, mx = (p->frame_w + h->g.LW - 1) / h->g.LW + 1;
+        if (1024ull * my * mx * (unsigned long long)std::max(p->frame_h, p->frame_w) >= (1ull << 31)) {
+            vti_set_error("vti_create: frame too large for the imgsz (mask moments would overflow a work unit's 32-bit sums)");
+            delete h;
+            return VTI_EINVAL;
+        }
+    }
     VTI_CUDA(cudaGetDevice(&h->device));
     VTI_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     const vti_geometry& g = h->g;

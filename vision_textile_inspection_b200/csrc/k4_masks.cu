@@ -71,7 +71,9 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
     // (2) cells
     const int ncc = ncw - 1;
     const float inv_ncc = 1.0f / (float)ncc;
-    long long m00 = 0, m10 = 0, m01 = 0;
+    // per-unit sums fit 32 bits (<= 1024 pixels x multiplicity^2 x frame size; vti_create refuses geometries that do not),
+    // so the warp reduction is three REDUX instructions instead of thirty 64-bit shuffle-adds
+    unsigned m00 = 0u, m10 = 0u, m01 = 0u;
     int cmin = INT_MAX, cmax = -1;
     uint32_t* __restrict__ mrow = EXPORT ? a.masks + ((size_t)b * a.max_det + k) * a.LH * (a.LW / 32) : nullptr;
     const int ncells = (nr - 1) * ncc;
@@ -164,13 +166,10 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
         }
     }
     // (3) warp reduction, one set of global atomics per unit
-    if (__any_sync(0xffffffffu, m00 > 0)) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m00 += __shfl_xor_sync(0xffffffffu, m00, o);
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
+    m00 = __reduce_add_sync(0xffffffffu, m00);
+    if (m00 > 0u) {
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
         cmin = __reduce_min_sync(0xffffffffu, cmin);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         if (lane == 0) {
