@@ -306,6 +306,12 @@ def test_errors_are_reported_not_raised_into_cuda():
         eng.preprocess(torch.zeros((1, 10, 10, 3), dtype=torch.uint8, device="cuda"))
     with pytest.raises(_lib.VtiError):
         eng.preprocess(torch.zeros((2, cfg.frame_h, cfg.frame_w, 3), dtype=torch.uint8, device="cuda"))  # B > max_batch
+    # a frame so large for its imgsz that a K4 work unit's 32-bit moment sums could overflow is refused at creation
+    calib = helpers.load_calib()
+    huge = EngineConfig(frame_h=16000, frame_w=16000, K=np.array(calib["camera_matrix"]), dist=np.array(calib["dist_coeffs"]),
+                        R=np.eye(3), t=np.array([0, 0, 0.1]), imgsz=640, max_batch=1)
+    with pytest.raises(_lib.VtiError, match="too large"):
+        InspectionEngine(huge)
 
 
 # ------------------------------------------------------------------------- BASELINE-size, size-independent properties

@@ -19,8 +19,10 @@
 //   (2) one lane per interpolation cell (the 4x4 output pixels between four prototype pixels).  A cell whose four
 //       corners are all > 0.5 (+margin) is entirely set, all < 0.5 (-margin) entirely clear -- bilinear weights are a
 //       convex combination -- and its contribution to m00/m10/m01, the column extent and the envelope is closed-form
-//       from prefix sums of the multiplicity tables; only boundary cells evaluate their 16 pixels.
-//   (3) warp reduction, one set of 64-bit global atomics per unit.
+//       from prefix sums of the multiplicity tables; only boundary cells evaluate their 16 pixels, and those are
+//       shared out over the warp two cells at a time, one pixel per lane (the mask edge crosses a unit as a line, so
+//       few lanes hold one).
+//   (3) warp reduction (three REDUX on 32-bit per-unit sums), one set of 64-bit global atomics per unit.
 // Optional bit-packed mask export: cells OR their bits into the (pre-zeroed) global mask words.
 // Bound: the prototype read (128 B per prototype pixel touched); algorithmic bytes 128*ph*pw per frame.
 #include <climits>
