@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 #ifndef VTI_FTX
 #define VTI_FTX 64
 #endif
+#ifndef VTI_K1_HSHARE
+#define VTI_K1_HSHARE 1
+#endif
 constexpr int FTX = VTI_FTX, FTY = VTI_FTY;  // fast-path output tile
 constexpr int FT_THREADS = VTI_FT_THREADS;
 constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration (prefetched)
@@ -507,7 +510,33 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
     const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
     const int ry0 = Y0 + j0 - a.top;
-    if (ry0 >= 0 && ry0 + RPT <= a.new_h) {                // no padding rows in this thread's strip (warp-uniform)
+    if (!AREA && VTI_K1_HSHARE && ry0 >= 0 && ry0 + RPT <= a.new_h) {
+        // Consecutive output rows of a shrink < 2x mostly share a source row (row i's lower tap row is row i + 1's upper
+        // one: 2 of 3 rows at 4/3): its H pass is kept in registers instead of being reloaded and recomputed.  The test
+        // is warp-uniform (the row taps are per tile row).
+        unsigned pb = 0u, pg = 0u, pr = 0u;                // (H pass >> 4) of the source row at byte offset `have`
+        int have = -1;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i, oi += a.LW) {
+            const int4 rt = s_rowtap[j0 + i];
+            if (rt.x != have) {
+                const unsigned t0 = *reinterpret_cast<const unsigned*>(col + rt.x), t1 = *reinterpret_cast<const unsigned*>(col + rt.x + 4);
+                const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
+                pb = __dp2a_lo(a01, bg, 0u) >> 4; pg = __dp2a_hi(a01, bg, 0u) >> 4; pr = __dp2a_lo(a01, rr, 0u) >> 4;
+            }
+            const unsigned t0 = *reinterpret_cast<const unsigned*>(col + rt.y), t1 = *reinterpret_cast<const unsigned*>(col + rt.y + 4);
+            const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
+            const unsigned nb = __dp2a_lo(a01, bg, 0u) >> 4, ng = __dp2a_hi(a01, bg, 0u) >> 4, nr = __dp2a_lo(a01, rr, 0u) >> 4;
+            const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
+            const unsigned qb = __dp2a_lo(__byte_perm(b0 * pb, b1 * nb, 0x7632), 0x0101u, 2u);
+            const unsigned qg = __dp2a_lo(__byte_perm(b0 * pg, b1 * ng, 0x7632), 0x0101u, 2u);
+            const unsigned qr = __dp2a_lo(__byte_perm(b0 * pr, b1 * nr, 0x7632), 0x0101u, 2u);
+            store_at(o0, oi, *reinterpret_cast<const float*>(divb + (qb & 0x3FCu)));
+            store_at(o1, oi, *reinterpret_cast<const float*>(divb + (qg & 0x3FCu)));
+            store_at(o2, oi, *reinterpret_cast<const float*>(divb + (qr & 0x3FCu)));
+            pb = nb; pg = ng; pr = nr; have = rt.y;
+        }
+    } else if (ry0 >= 0 && ry0 + RPT <= a.new_h) {         // no padding rows in this thread's strip (warp-uniform)
 #pragma unroll 4
         for (int i = 0; i < RPT; ++i, oi += a.LW) {
             const int4 rt = s_rowtap[j0 + i];
