@@ -68,7 +68,7 @@ def load():
     if _lib is not None:
         return _lib
     from . import build
-    if build.needs_build():
+    if not os.environ.get("VTI_NO_BUILD") and build.needs_build():   # (VTI_NO_BUILD: tuning sweeps load prebuilt variants)
         build.build_lib()
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64

@@ -229,6 +229,12 @@ class StitchMeasurementApp:
         return sd, sw
 
     def _finish(self, r) -> dict:
+        if int(r["status"]) & _lib.ST_OVERFLOW:
+            # more confidence-passing anchors than the handle's candidate capacity: the kept subset is not the
+            # top-scoring one (Ultralytics keeps the best max_nms) -- never silent
+            import warnings
+            warnings.warn(f"vti: candidate list overflow ({int(r['n_cand'])} candidates): raise max_candidates or conf",
+                          RuntimeWarning, stacklevel=2)
         status = int(r["status"]) & 0xFF
         if status in _ERRORS:
             return {"edge_distance_mm": None, "stitch_width_mm": None, "stitch_count": 0,

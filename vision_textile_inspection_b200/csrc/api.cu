@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "vti_internal.h"
 
@@ -19,6 +22,22 @@ int vti_k4_prepare();
 
 static thread_local std::string g_err;
 void vti_set_error(const std::string& s) { g_err = s; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION (per device), not to a handle: a later
+// handle with a smaller need must not lower it under an earlier handle that still launches with more.  Only raise.
+int vti_raise_dyn_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    int dev = 0;
+    VTI_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = cur[std::make_pair(dev, func)];
+    if (bytes > have) {
+        VTI_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return VTI_OK;
+}
 
 extern "C" const char* vti_last_error(void) { return g_err.c_str(); }
 extern "C" int vti_abi_version(void) { return 1; }
@@ -190,9 +209,11 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
         vti_set_error("vti_create: vti_params.struct_size mismatch (ABI)");
         return VTI_EINVAL;
     }
-    if (p->nc < 1 || p->nc > 255 || p->max_det < 1 || p->max_det > 1024 || p->max_batch < 1 || p->neighborhood < 0 ||
-        p->neighborhood > 7 || (p->variant != 0 && p->variant != 1)) {
-        vti_set_error("vti_create: parameter out of range (nc 1..255, max_det 1..1024, neighborhood 0..7, variant 0/1)");
+    // nc: K2 packs the class into the top byte of a candidate key; max_batch: K3 packs the frame index into 15 bits
+    if (p->nc < 1 || p->nc > 255 || p->max_det < 1 || p->max_det > 1024 || p->max_batch < 1 || p->max_batch > 32767 ||
+        p->neighborhood < 0 || p->neighborhood > 7 || (p->variant != 0 && p->variant != 1)) {
+        vti_set_error("vti_create: parameter out of range (nc 1..255, max_det 1..1024, max_batch 1..32767, "
+                      "neighborhood 0..7, variant 0/1)");
         return VTI_EINVAL;
     }
     int ndev = 0;

@@ -304,16 +304,76 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 #ifndef VTI_K1_HSHARE
 #define VTI_K1_HSHARE 1
 #endif
+// round-2 instruction cuts (each can be switched off for A/B runs: tools/k1_sweep.sh)
+#ifndef VTI_K1_LUT8      // 8-byte remap entries (weights pre-decoded) + one raw pitch per handle (a uniform register)
+#define VTI_K1_LUT8 0
+#endif
+#ifndef VTI_K1_FIXPITCH  // one raw-box row pitch per handle, an immediate in the remap loads when it is K1_RAWP
+#define VTI_K1_FIXPITCH 1
+#endif
+#ifndef VTI_K1_MULHI     // V pass of the resize: (b * P) >> 16 as one mad.hi on b << 16
+#define VTI_K1_MULHI 0
+#endif
+#ifndef VTI_K1_LWT       // output row pitch as a template constant: plane stores take immediate offsets
+#define VTI_K1_LWT 1
+#endif
+#ifndef VTI_K1_STAGE2    // staging: (row, group) per lane by shifts, two rows per warp pass, interior boxes unchecked
+#define VTI_K1_STAGE2 0
+#endif
+#ifndef VTI_K1_DIVFMA    // x / 255 as FMUL + FFMA on split constants (exact for 0..255) instead of a shared-memory table
+#define VTI_K1_DIVFMA 1
+#endif
+#ifndef VTI_K1_PADROWS   // strips that contain letterbox padding rows stay on the register-sharing resize path
+#define VTI_K1_PADROWS 1
+#endif
 constexpr int FTX = VTI_FTX, FTY = VTI_FTY;  // fast-path output tile
 constexpr int FT_THREADS = VTI_FT_THREADS;
 constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration (prefetched)
 constexpr int FT_MAXROWS = 2 * FTY + 2, FT_MAXCOLS = 2 * FTX + 2;
+constexpr int K1_RAWP = 112;    // raw-box row pitch (words) baked into the remap kernel when no tile needs more
+
+// float32(i) / 255.0f (a true division, IEEE round-to-nearest), as bit patterns: i/255 for the 256 uint8 values.
+// Generated with numpy float32; tests/test_gpu_parity.py::test_k1_bit_exact compares every value against cv2 + torch.
+__device__ const unsigned g_div255_bits[256] = {
+    0x00000000u, 0x3b808081u, 0x3c008081u, 0x3c40c0c1u, 0x3c808081u, 0x3ca0a0a1u, 0x3cc0c0c1u, 0x3ce0e0e1u,
+    0x3d008081u, 0x3d109091u, 0x3d20a0a1u, 0x3d30b0b1u, 0x3d40c0c1u, 0x3d50d0d1u, 0x3d60e0e1u, 0x3d70f0f1u,
+    0x3d808081u, 0x3d888889u, 0x3d909091u, 0x3d989899u, 0x3da0a0a1u, 0x3da8a8a9u, 0x3db0b0b1u, 0x3db8b8b9u,
+    0x3dc0c0c1u, 0x3dc8c8c9u, 0x3dd0d0d1u, 0x3dd8d8d9u, 0x3de0e0e1u, 0x3de8e8e9u, 0x3df0f0f1u, 0x3df8f8f9u,
+    0x3e008081u, 0x3e048485u, 0x3e088889u, 0x3e0c8c8du, 0x3e109091u, 0x3e149495u, 0x3e189899u, 0x3e1c9c9du,
+    0x3e20a0a1u, 0x3e24a4a5u, 0x3e28a8a9u, 0x3e2cacadu, 0x3e30b0b1u, 0x3e34b4b5u, 0x3e38b8b9u, 0x3e3cbcbdu,
+    0x3e40c0c1u, 0x3e44c4c5u, 0x3e48c8c9u, 0x3e4ccccdu, 0x3e50d0d1u, 0x3e54d4d5u, 0x3e58d8d9u, 0x3e5cdcddu,
+    0x3e60e0e1u, 0x3e64e4e5u, 0x3e68e8e9u, 0x3e6cecedu, 0x3e70f0f1u, 0x3e74f4f5u, 0x3e78f8f9u, 0x3e7cfcfdu,
+    0x3e808081u, 0x3e828283u, 0x3e848485u, 0x3e868687u, 0x3e888889u, 0x3e8a8a8bu, 0x3e8c8c8du, 0x3e8e8e8fu,
+    0x3e909091u, 0x3e929293u, 0x3e949495u, 0x3e969697u, 0x3e989899u, 0x3e9a9a9bu, 0x3e9c9c9du, 0x3e9e9e9fu,
+    0x3ea0a0a1u, 0x3ea2a2a3u, 0x3ea4a4a5u, 0x3ea6a6a7u, 0x3ea8a8a9u, 0x3eaaaaabu, 0x3eacacadu, 0x3eaeaeafu,
+    0x3eb0b0b1u, 0x3eb2b2b3u, 0x3eb4b4b5u, 0x3eb6b6b7u, 0x3eb8b8b9u, 0x3ebababbu, 0x3ebcbcbdu, 0x3ebebebfu,
+    0x3ec0c0c1u, 0x3ec2c2c3u, 0x3ec4c4c5u, 0x3ec6c6c7u, 0x3ec8c8c9u, 0x3ecacacbu, 0x3ecccccdu, 0x3ecececfu,
+    0x3ed0d0d1u, 0x3ed2d2d3u, 0x3ed4d4d5u, 0x3ed6d6d7u, 0x3ed8d8d9u, 0x3edadadbu, 0x3edcdcddu, 0x3edededfu,
+    0x3ee0e0e1u, 0x3ee2e2e3u, 0x3ee4e4e5u, 0x3ee6e6e7u, 0x3ee8e8e9u, 0x3eeaeaebu, 0x3eececedu, 0x3eeeeeefu,
+    0x3ef0f0f1u, 0x3ef2f2f3u, 0x3ef4f4f5u, 0x3ef6f6f7u, 0x3ef8f8f9u, 0x3efafafbu, 0x3efcfcfdu, 0x3efefeffu,
+    0x3f008081u, 0x3f018182u, 0x3f028283u, 0x3f038384u, 0x3f048485u, 0x3f058586u, 0x3f068687u, 0x3f078788u,
+    0x3f088889u, 0x3f09898au, 0x3f0a8a8bu, 0x3f0b8b8cu, 0x3f0c8c8du, 0x3f0d8d8eu, 0x3f0e8e8fu, 0x3f0f8f90u,
+    0x3f109091u, 0x3f119192u, 0x3f129293u, 0x3f139394u, 0x3f149495u, 0x3f159596u, 0x3f169697u, 0x3f179798u,
+    0x3f189899u, 0x3f19999au, 0x3f1a9a9bu, 0x3f1b9b9cu, 0x3f1c9c9du, 0x3f1d9d9eu, 0x3f1e9e9fu, 0x3f1f9fa0u,
+    0x3f20a0a1u, 0x3f21a1a2u, 0x3f22a2a3u, 0x3f23a3a4u, 0x3f24a4a5u, 0x3f25a5a6u, 0x3f26a6a7u, 0x3f27a7a8u,
+    0x3f28a8a9u, 0x3f29a9aau, 0x3f2aaaabu, 0x3f2babacu, 0x3f2cacadu, 0x3f2dadaeu, 0x3f2eaeafu, 0x3f2fafb0u,
+    0x3f30b0b1u, 0x3f31b1b2u, 0x3f32b2b3u, 0x3f33b3b4u, 0x3f34b4b5u, 0x3f35b5b6u, 0x3f36b6b7u, 0x3f37b7b8u,
+    0x3f38b8b9u, 0x3f39b9bau, 0x3f3ababbu, 0x3f3bbbbcu, 0x3f3cbcbdu, 0x3f3dbdbeu, 0x3f3ebebfu, 0x3f3fbfc0u,
+    0x3f40c0c1u, 0x3f41c1c2u, 0x3f42c2c3u, 0x3f43c3c4u, 0x3f44c4c5u, 0x3f45c5c6u, 0x3f46c6c7u, 0x3f47c7c8u,
+    0x3f48c8c9u, 0x3f49c9cau, 0x3f4acacbu, 0x3f4bcbccu, 0x3f4ccccdu, 0x3f4dcdceu, 0x3f4ececfu, 0x3f4fcfd0u,
+    0x3f50d0d1u, 0x3f51d1d2u, 0x3f52d2d3u, 0x3f53d3d4u, 0x3f54d4d5u, 0x3f55d5d6u, 0x3f56d6d7u, 0x3f57d7d8u,
+    0x3f58d8d9u, 0x3f59d9dau, 0x3f5adadbu, 0x3f5bdbdcu, 0x3f5cdcddu, 0x3f5ddddeu, 0x3f5ededfu, 0x3f5fdfe0u,
+    0x3f60e0e1u, 0x3f61e1e2u, 0x3f62e2e3u, 0x3f63e3e4u, 0x3f64e4e5u, 0x3f65e5e6u, 0x3f66e6e7u, 0x3f67e7e8u,
+    0x3f68e8e9u, 0x3f69e9eau, 0x3f6aeaebu, 0x3f6bebecu, 0x3f6cecedu, 0x3f6dedeeu, 0x3f6eeeefu, 0x3f6feff0u,
+    0x3f70f0f1u, 0x3f71f1f2u, 0x3f72f2f3u, 0x3f73f3f4u, 0x3f74f4f5u, 0x3f75f5f6u, 0x3f76f6f7u, 0x3f77f7f8u,
+    0x3f78f8f9u, 0x3f79f9fau, 0x3f7afafbu, 0x3f7bfbfcu, 0x3f7cfcfdu, 0x3f7dfdfeu, 0x3f7efeffu, 0x3f800000u,
+};
 
 struct K1FastArgs {
     const uint8_t* frames;
     float* out;
     const int4* tile_hdr;       // [tiles][2]: (bx0, by0, bw, bh), (r_lo, c_lo, nrows, ncols)
-    const unsigned* lut;        // [tiles][lut_stride]   (REMAP only)
+    const unsigned* lut;        // [tiles][lut_stride] entries of 4 bytes (8 with VTI_K1_LUT8)   (REMAP only)
     const int32_t* tap_x_idx;   // [new_w]
     const int16_t* tap_x_a;     // [new_w][2]
     const int32_t* tap_y_i;     // [new_h][2]
@@ -323,6 +383,7 @@ struct K1FastArgs {
     int pitch_u, rows_u;
     int und_words;              // words reserved for the footprint buffer (multiple of FT_CHUNK, > rows_u * pitch_u)
     int lut_stride;             // entries per tile (multiple of FT_CHUNK)
+    int raw_pitch;              // VTI_K1_LUT8: words per row of the raw box in shared memory (same for every tile)
 };
 
 // Stage rows [y0, y0+nr) x 8-pixel groups [x0, x0 + 8*ng) of the frame as packed words (B | G<<8 | R<<16, byte 3 = 0);
@@ -332,7 +393,7 @@ struct K1FastArgs {
 // thread; v3.1 waited on one group at a time and spent 40 % of its stall samples here.
 constexpr int STAGE_R = 3;
 __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
-                                          unsigned* dst, int tid, int flip) {
+                                          unsigned* dst, int tid, int flip, int pitch = 0) {
     const int total = ng * nr;
     const float inv_ng = 1.0f / (float)ng;
     // PRMT selectors: byte 4 (of the zero second operand) clears the top byte; the flipped variants reverse B and R
@@ -341,6 +402,7 @@ __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int
     for (int base = tid; base < total; base += STAGE_R * FT_THREADS) {
         uint2 q[STAGE_R][3];
         bool ok[STAGE_R];
+        int dofs[STAGE_R];
 #pragma unroll
         for (int k = 0; k < STAGE_R; ++k) {
             const int i = base + k * FT_THREADS;
@@ -348,6 +410,7 @@ __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int
             const int r = (int)(((float)i + 0.5f) * inv_ng);
             const int g = i - r * ng;
             const int y = y0 + r, x = x0 + 8 * g;
+            dofs[k] = pitch ? r * pitch + 8 * g : 8 * i;   // rows at a fixed pitch (>= 8 ng) or packed
             ok[k] = (i < total) && ((unsigned)y < (unsigned)h) && ((unsigned)x < (unsigned)w);
             const unsigned off = ok[k] ? (unsigned)(y * w + x) * 3u : 0u;        // frames are < 2^31 bytes
             const uint2* __restrict__ src = reinterpret_cast<const uint2*>(frame + off);
@@ -369,9 +432,60 @@ __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int
                 hi.z = __byte_perm(__funnelshift_r(w4, w5, 16), 0u, sel_lo);
                 hi.w = __byte_perm(w5, 0u, sel_hi);
             }
-            uint4* d = reinterpret_cast<uint4*>(dst + 8 * i);
+            uint4* d = reinterpret_cast<uint4*>(dst + dofs[k]);
             d[0] = lo; d[1] = hi;
         }
+    }
+}
+
+// Round-2 staging (VTI_K1_STAGE2).  K1 is bound by L1 data-pipe wavefronts, so the staging is organised around them:
+// a lane owns ONE 16-byte shared chunk = 4 pixels = 12 source bytes (three 32-bit loads; x0 % 4 == 0 and w % 4 == 0
+// keep them aligned and inside the row), a warp owns one box row per pass, so its single STS.128 writes consecutive
+// chunks: 4 wavefronts per 512 bytes, the minimum (the 8-pixel form writes two chunks per lane: 2-way bank conflicts,
+// 7.7 wavefronts per store measured).  The (row, chunk) of a lane costs no division.  The P passes of a box (8 rows
+// each; P = 4 or 3, picked per CTA) are straight-line code with 3 P loads in flight per lane before the first unpack;
+// only the shared store of a row past the box is predicated off.  A chunk outside the image (cv2.remap's
+// BORDER_CONSTANT zero margin) loads from a block of zeros instead: no zeroing instructions.
+__device__ const unsigned g_zero12[4] = {0u, 0u, 0u, 0u};
+
+template <int P>
+__device__ __forceinline__ void stage_rows(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int nc, int nr,
+                                           int rb0, unsigned* dst, int pitch, int tid, unsigned sel_lo, unsigned sel_hi) {
+    const int lane = tid & 31;
+    constexpr int NW = FT_THREADS / 32;
+    const int rb = rb0 + (tid >> 5);
+    for (int c = lane; c < nc; c += 32) {
+        const int x = x0 + 4 * c;
+        const bool xin = (unsigned)x < (unsigned)w;
+        unsigned q[P][3];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const int r = rb + NW * k, y = y0 + r;
+            const bool ok = (r < nr) && xin && ((unsigned)y < (unsigned)h);
+            const unsigned* __restrict__ src = ok ? reinterpret_cast<const unsigned*>(frame + (unsigned)(y * w + x) * 3u)
+                                                  : g_zero12;                             // frames are < 2^31 bytes
+            q[k][0] = __ldg(src); q[k][1] = __ldg(src + 1); q[k][2] = __ldg(src + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const int r = rb + NW * k;
+            uint4 v;
+            v.x = __byte_perm(q[k][0], 0u, sel_lo);
+            v.y = __byte_perm(__funnelshift_r(q[k][0], q[k][1], 24), 0u, sel_lo);
+            v.z = __byte_perm(__funnelshift_r(q[k][1], q[k][2], 16), 0u, sel_lo);
+            v.w = __byte_perm(q[k][2], 0u, sel_hi);
+            if (r < nr) *reinterpret_cast<uint4*>(dst + r * pitch + 4 * c) = v;
+        }
+    }
+}
+// ng = 8-pixel groups per row (the plan sizes boxes in groups), nr rows
+__device__ __forceinline__ void stage_box2(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
+                                           unsigned* dst, int pitch, int tid, int flip) {
+    const unsigned sel_lo = flip ? 0x4012u : 0x4210u, sel_hi = flip ? 0x4123u : 0x4321u;
+    constexpr int RPP = FT_THREADS / 32;                   // rows per pass
+    for (int rb0 = 0; rb0 < nr;) {                          // CTA-uniform control flow
+        if (nr - rb0 > 3 * RPP) { stage_rows<4>(frame, h, w, x0, y0, 2 * ng, nr, rb0, dst, pitch, tid, sel_lo, sel_hi); rb0 += 4 * RPP; }
+        else { stage_rows<3>(frame, h, w, x0, y0, 2 * ng, nr, rb0, dst, pitch, tid, sel_lo, sel_hi); rb0 += 3 * RPP; }
     }
 }
 
@@ -395,12 +509,62 @@ __device__ __forceinline__ unsigned remap_fast(const unsigned char* raw, unsigne
     return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);           // bytes 3 of b, g, r are 0
 }
 
+// 32-bit shared-window addresses and ld.shared: the address of a tap is ONE integer add away from the per-thread
+// base (generic pointers cost an extra instruction per load to re-add the window base).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// 4-byte entry (off16 | fy | fx) on shared-window addresses; RAWP_T > 0: second row at an immediate offset
+template <int RAWP_T>
+__device__ __forceinline__ unsigned remap_fast4(unsigned raw, unsigned e, unsigned bw4) {
+    const unsigned p0 = raw + (e >> 16);
+    const unsigned fx = e & 0xFFu, fy = __byte_perm(e, 0, 0x4441);
+    unsigned t00 = lds32<0>(p0), t01 = lds32<4>(p0), t10, t11;
+    if (RAWP_T > 0) { t10 = lds32<4 * RAWP_T>(p0); t11 = lds32<4 * RAWP_T + 4>(p0); }
+    else { t10 = lds32<0>(p0 + bw4); t11 = lds32<4>(p0 + bw4); }
+    const unsigned wy0 = fy * 0xFFFFFFFFu + 32u;               // 32 - fy, as a multiply-add (FMA pipe)
+    const unsigned wxb = fx * 255u + 32u;                      // (32 - fx) | fx << 8
+    const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
+    const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
+    const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
+    const unsigned b = __dp2a_lo(vB, wxb, 512u) * 64u;
+    const unsigned g = __dp2a_lo(vG, wxb, 512u) * 64u;
+    const unsigned r = __dp2a_lo(vR, wxb, 512u) * 64u;
+    return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);
+}
+
+// 8-byte entry: x = byte offset of the 2x2 neighbourhood << 16 | fx << 8 | (32 - fx)   (dp2a reads bytes 0, 1 as they are)
+//               y = fy << 16 | (32 - fy)
+// RAWP_T > 0: the raw box has that many words per row for every tile, so the second row is an immediate offset.
+template <int RAWP_T>
+__device__ __forceinline__ unsigned remap_fast8(unsigned raw, uint2 e, unsigned bw4) {
+    const unsigned p0 = raw + (e.x >> 16);
+    unsigned t00 = lds32<0>(p0), t01 = lds32<4>(p0), t10, t11;
+    if (RAWP_T > 0) { t10 = lds32<4 * RAWP_T>(p0); t11 = lds32<4 * RAWP_T + 4>(p0); }
+    else { t10 = lds32<0>(p0 + bw4); t11 = lds32<4>(p0 + bw4); }
+    const unsigned wy0 = e.y & 0xFFFFu, fy = e.y >> 16;
+    const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
+    const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
+    const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
+    const unsigned b = __dp2a_lo(vB, e.x, 512u) * 64u;
+    const unsigned g = __dp2a_lo(vG, e.x, 512u) * 64u;
+    const unsigned r = __dp2a_lo(vR, e.x, 512u) * 64u;
+    return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);
+}
+
 // base[idx] = v with the address formed by ONE mad.wide (FMA pipe) -- the compiler's own 64-bit index arithmetic
 // costs four ALU-pipe instructions per store, and the ALU pipe is what bounds this kernel.
 __device__ __forceinline__ void store_at(float* base, int idx, float v) {
     asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %1, 4, %0;\n\tst.global.f32 [a], %2;\n\t}"
                  :: "l"(base), "r"(idx), "f"(v) : "memory");
 }
+
+__device__ __forceinline__ float div255_q(unsigned q, const unsigned char* divb);
 
 // One output pixel (3 channels) of cv2.resize's fixed-point bilinear (or the exact-2x area average) + /255.
 template <bool AREA>
@@ -422,12 +586,97 @@ __device__ __forceinline__ void resize_px(const unsigned char* p0, const unsigne
         qg = __dp2a_lo(__byte_perm(b0 * (S0g >> 4), b1 * (S1g >> 4), 0x7632), 0x0101u, 2u);
         qr = __dp2a_lo(__byte_perm(b0 * (S0r >> 4), b1 * (S1r >> 4), 0x7632), 0x0101u, 2u);
     }
-    v0 = *reinterpret_cast<const float*>(divb + (qb & 0x3FCu));
-    v1 = *reinterpret_cast<const float*>(divb + (qg & 0x3FCu));
-    v2 = *reinterpret_cast<const float*>(divb + (qr & 0x3FCu));
+    v0 = div255_q(qb, divb);
+    v1 = div255_q(qg, divb);
+    v2 = div255_q(qr, divb);
 }
 
-template <bool REMAP, bool AREA>
+// mul.hi kept apart from the following add (as mad.hi, SASS IMAD.HI takes a 64-bit addend whose low word has to be
+// zeroed first: one extra move per use), and a three-input add (IADD3) for the two products and the rounding constant.
+__device__ __forceinline__ unsigned mulhi_nf(unsigned a, unsigned b) {
+    unsigned d;
+    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned add3(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// float32(v) / 255.0f for q = 4 v + (0..3), v in 0..255, WITHOUT the table: x = float(4 v) is exact, 1/1020 is split
+// into c1 + c2 (c1 = RN(1/1020), c2 = RN(1/1020 - c1)), t = RN(x c2), y = RN(x c1 + t) (one FMA).  x c1 + x c2 differs
+// from the quotient by < 2^-48 relative, far below the distance of any v / 255 to a rounding boundary: all 256 values
+// were checked against numpy's float32 division with exact rational arithmetic (tools/check_div255.py), and
+// tests/test_gpu_parity.py::test_k1_bit_exact compares the kernel's output with cv2 + torch bit for bit.
+// K1 is bound by the L1 data pipe (shared-memory wavefronts), not by issue slots: 2 more instructions per value on the
+// otherwise idle FP32 pipe replace one table LDS (1.34 wavefronts measured, values in a warp collide on banks).
+__device__ __forceinline__ float div255_q(unsigned q, const unsigned char* divb) {
+#if VTI_K1_DIVFMA
+    const float x = __uint2float_rn(q & 0x3FCu);
+    return __fmaf_rn(x, __uint_as_float(0x3a808081u), __fmul_rn(x, __uint_as_float(0xae7efeffu)));
+#else
+    return *reinterpret_cast<const float*>(divb + (q & 0x3FCu));
+#endif
+}
+
+// One plane store.  LW_T > 0: the row pitch is a compile-time constant, the address is base + immediate.
+template <int LW_T>
+__device__ __forceinline__ void store_px(float* base, int i, int oi, float v) {
+    if (LW_T > 0) base[i * LW_T] = v;
+    else store_at(base, oi, v);
+}
+
+// Resize of one thread's strip of RPT output rows (one column, three planes) with the H pass of shared source rows
+// kept in registers.  Consecutive output rows of a shrink < 2x mostly share a source row (row i's lower tap row is
+// row i + 1's upper one: 2 of 3 rows at 4/3), so its H pass is not reloaded and recomputed; the test is warp-uniform
+// (the row taps are per tile row).  CHECK: the strip may hold letterbox padding rows (offset -2) or end early.
+template <int LW_T, bool CHECK>
+__device__ __forceinline__ void resize_strip(const int4* rowtap, unsigned col, unsigned a01,
+                                             const unsigned char* divb, float* o0, float* o1, float* o2, int LW,
+                                             int n_out, float pad) {
+    constexpr int RPT = FTY / (FT_THREADS / FTX);
+    unsigned pb = 0u, pg = 0u, pr = 0u;                    // (H pass >> 4) of the source row at byte offset `have`
+    int have = -1, oi = 0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i, oi += LW) {
+        const int4 rt = rowtap[i];
+        if (CHECK) {
+            if (i >= n_out) break;
+            if (rt.x < 0) {
+                store_px<LW_T>(o0, i, oi, pad); store_px<LW_T>(o1, i, oi, pad); store_px<LW_T>(o2, i, oi, pad);
+                continue;
+            }
+        }
+        if (rt.x != have) {
+            const unsigned t0 = lds32<0>(col + rt.x), t1 = lds32<4>(col + rt.x);
+            const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
+            pb = __dp2a_lo(a01, bg, 0u) >> 4; pg = __dp2a_hi(a01, bg, 0u) >> 4; pr = __dp2a_lo(a01, rr, 0u) >> 4;
+        }
+        const unsigned t0 = lds32<0>(col + rt.y), t1 = lds32<4>(col + rt.y);
+        const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
+        const unsigned nb = __dp2a_lo(a01, bg, 0u) >> 4, ng = __dp2a_hi(a01, bg, 0u) >> 4, nr = __dp2a_lo(a01, rr, 0u) >> 4;
+        const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
+        unsigned qb, qg, qr;
+#if VTI_K1_MULHI
+        // ((b0 P0) >> 16) + ((b1 P1) >> 16) + 2 with b pre-shifted by 16: two mad.hi per channel
+        qb = add3(mulhi_nf(b0, pb), mulhi_nf(b1, nb), 2u);
+        qg = add3(mulhi_nf(b0, pg), mulhi_nf(b1, ng), 2u);
+        qr = add3(mulhi_nf(b0, pr), mulhi_nf(b1, nr), 2u);
+#else
+        // PRMT takes both >> 16 at once, dp2a adds them.  The plan guarantees b0 + b1 <= 2049: no saturation needed.
+        qb = __dp2a_lo(__byte_perm(b0 * pb, b1 * nb, 0x7632), 0x0101u, 2u);
+        qg = __dp2a_lo(__byte_perm(b0 * pg, b1 * ng, 0x7632), 0x0101u, 2u);
+        qr = __dp2a_lo(__byte_perm(b0 * pr, b1 * nr, 0x7632), 0x0101u, 2u);
+#endif
+        store_px<LW_T>(o0, i, oi, div255_q(qb, divb));
+        store_px<LW_T>(o1, i, oi, div255_q(qg, divb));
+        store_px<LW_T>(o2, i, oi, div255_q(qr, divb));
+        pb = nb; pg = ng; pr = nr; have = rt.y;
+    }
+}
+
+template <bool REMAP, bool AREA, int LW_T, int RAWP_T>
 __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const K1FastArgs a) {
     extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [und_words], then the raw box (REMAP)
     __shared__ float s_div[256];
@@ -437,21 +686,23 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     const int X0 = blockIdx.x * FTX, Y0 = blockIdx.y * FTY;
     const int b = blockIdx.z;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int LW = LW_T > 0 ? LW_T : a.LW;
     const uint8_t* __restrict__ frame = a.frames + (size_t)b * a.h * a.w * 3;
-    float* __restrict__ out = a.out + (size_t)b * 3 * a.LH * a.LW;
+    float* __restrict__ out = a.out + (size_t)b * 3 * a.LH * LW;
     unsigned* s_und = s_dyn;
 
     const int4 h0 = __ldg(a.tile_hdr + 2 * tile), h1 = __ldg(a.tile_hdr + 2 * tile + 1);
     const int r_lo = h1.x, c_lo = h1.y, nrows = h1.z;
-    for (int i = tid; i < 256; i += FT_THREADS) s_div[i] = __fdiv_rn((float)i, 255.0f);
+    for (int i = tid; i < 256; i += FT_THREADS) s_div[i] = __uint_as_float(g_div255_bits[i]);
     if (tid < FTY) {
         const int ry = Y0 + tid - a.top;
-        int4 t = make_int4(0, 0, 0, 0);
+        int4 t = make_int4(-2, -2, 0, 0);                   // padding row (never equal to a real row offset)
         if (ry >= 0 && ry < a.new_h && nrows > 0) {
             t.x = (a.tap_y_i[2 * ry] - r_lo) * a.pitch_u * 4;
             t.y = (a.tap_y_i[2 * ry + 1] - r_lo) * a.pitch_u * 4;
             t.z = a.tap_y_b[2 * ry];
             t.w = a.tap_y_b[2 * ry + 1];
+            if (VTI_K1_MULHI && !AREA) { t.z <<= 16; t.w <<= 16; }      // b <= 2048: mad.hi operands
         }
         s_rowtap[tid] = t;
     }
@@ -459,29 +710,54 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     // ------------------------------------------------------------------------------------------- stage (+ remap)
     if (nrows > 0) {
         if (!REMAP) {
+#if VTI_K1_STAGE2
+            stage_box2(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 3, nrows, s_und, a.pitch_u, tid, a.flip);
+#else
             stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 3, nrows, s_und, tid, a.flip);
+#endif
         } else {
             unsigned* s_raw = s_dyn + a.und_words;
-            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, tid, a.flip);
+#if VTI_K1_STAGE2
+            const int rp = VTI_K1_FIXPITCH ? (RAWP_T > 0 ? RAWP_T : a.raw_pitch) : h0.z;
+            stage_box2(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, rp, tid, a.flip);
+#else
+            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, tid, a.flip, VTI_K1_FIXPITCH ? a.raw_pitch : 0);
+#endif
             __syncthreads();
             const unsigned char* raw = reinterpret_cast<const unsigned char*>(s_raw);
-            const unsigned bw4 = (unsigned)h0.z * 4u;
-            const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
             unsigned* dst = s_und + tid;
             const int total = nrows * a.pitch_u;
             const int n_it = total / FT_CHUNK;                 // whole chunks; table and buffer are padded
+            const int rem = total - n_it * FT_CHUNK;
+            const unsigned raw8 = smem_addr(s_raw);
+#if VTI_K1_LUT8
+            const unsigned bw4 = (unsigned)a.raw_pitch * 4u;
+            const uint2* __restrict__ lut = reinterpret_cast<const uint2*>(a.lut) + (size_t)tile * a.lut_stride + tid;
+            uint2 e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
+            for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
+                lut += FT_CHUNK;                               // next entries in flight while these are computed
+                const uint2 n0 = __ldg(lut), n1 = __ldg(lut + FT_THREADS);       // (the table has one spare chunk)
+                dst[0] = remap_fast8<RAWP_T>(raw8, e0, bw4);
+                dst[FT_THREADS] = remap_fast8<RAWP_T>(raw8, e1, bw4);
+                e0 = n0; e1 = n1;
+            }
+            if (tid < rem) dst[0] = remap_fast8<RAWP_T>(raw8, e0, bw4);
+            if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast8<RAWP_T>(raw8, e1, bw4);
+#else
+            const unsigned bw4 = (unsigned)(VTI_K1_FIXPITCH ? a.raw_pitch : h0.z) * 4u;
+            const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
             unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
             for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
                 lut += FT_CHUNK;                               // next entries in flight while these are computed
                 const unsigned n0 = __ldg(lut), n1 = __ldg(lut + FT_THREADS);   // (the table has one spare chunk)
-                dst[0] = remap_fast(raw, e0, bw4);
-                dst[FT_THREADS] = remap_fast(raw, e1, bw4);
+                dst[0] = remap_fast4<RAWP_T>(raw8, e0, bw4);
+                dst[FT_THREADS] = remap_fast4<RAWP_T>(raw8, e1, bw4);
                 e0 = n0; e1 = n1;
             }
             // tail of the footprint: only the warps that still have cells (a 44 x 87 footprint leaves 244 of 512)
-            const int rem = total - n_it * FT_CHUNK;
-            if (tid < rem) dst[0] = remap_fast(raw, e0, bw4);
-            if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast(raw, e1, bw4);
+            if (tid < rem) dst[0] = remap_fast4<RAWP_T>(raw8, e0, bw4);
+            if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast4<RAWP_T>(raw8, e1, bw4);
+#endif
         }
     }
     __syncthreads();
@@ -489,19 +765,22 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     // ----------------------------------------------------------------------------------------------- resize
     const float pad = s_div[114];
     const int X = X0 + (tid & (FTX - 1));
-    if (X >= a.LW) return;
+    if (X >= LW) return;
     constexpr int RPT = FTY / (FT_THREADS / FTX);          // rows per thread
     const int j0 = (tid / FTX) * RPT;
-    const size_t plane = (size_t)a.LH * a.LW;
-    float* __restrict__ o0 = out + (size_t)(Y0 + j0) * a.LW + X;     // three plane pointers + one 32-bit row offset
+    const size_t plane = (size_t)a.LH * LW;
+    float* __restrict__ o0 = out + (size_t)(Y0 + j0) * LW + X;       // three plane pointers + one 32-bit row offset
     float* __restrict__ o1 = o0 + plane;
     float* __restrict__ o2 = o1 + plane;
     int oi = 0;
     const int rx = X - a.left;
-    if (rx < 0 || rx >= a.new_w || nrows == 0) {           // padding column
+    const int ry0 = Y0 + j0 - a.top;
+    // rows of this thread's strip that exist in the letterboxed frame, then those that are resized image rows
+    const int n_out = min(RPT, a.LH - (Y0 + j0));
+    if (rx < 0 || rx >= a.new_w || nrows == 0 || ry0 + n_out <= 0 || ry0 >= a.new_h) {     // nothing but padding
 #pragma unroll
-        for (int i = 0; i < RPT; ++i, oi += a.LW) {
-            store_at(o0, oi, pad); store_at(o1, oi, pad); store_at(o2, oi, pad);
+        for (int i = 0; i < RPT; ++i, oi += LW) {
+            if (i < n_out) { store_px<LW_T>(o0, i, oi, pad); store_px<LW_T>(o1, i, oi, pad); store_px<LW_T>(o2, i, oi, pad); }
         }
         return;
     }
@@ -509,48 +788,18 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
     const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
     const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
-    const int ry0 = Y0 + j0 - a.top;
-    if (!AREA && VTI_K1_HSHARE && ry0 >= 0 && ry0 + RPT <= a.new_h) {
-        // Consecutive output rows of a shrink < 2x mostly share a source row (row i's lower tap row is row i + 1's upper
-        // one: 2 of 3 rows at 4/3): its H pass is kept in registers instead of being reloaded and recomputed.  The test
-        // is warp-uniform (the row taps are per tile row).
-        unsigned pb = 0u, pg = 0u, pr = 0u;                // (H pass >> 4) of the source row at byte offset `have`
-        int have = -1;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i, oi += a.LW) {
-            const int4 rt = s_rowtap[j0 + i];
-            if (rt.x != have) {
-                const unsigned t0 = *reinterpret_cast<const unsigned*>(col + rt.x), t1 = *reinterpret_cast<const unsigned*>(col + rt.x + 4);
-                const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
-                pb = __dp2a_lo(a01, bg, 0u) >> 4; pg = __dp2a_hi(a01, bg, 0u) >> 4; pr = __dp2a_lo(a01, rr, 0u) >> 4;
-            }
-            const unsigned t0 = *reinterpret_cast<const unsigned*>(col + rt.y), t1 = *reinterpret_cast<const unsigned*>(col + rt.y + 4);
-            const unsigned bg = __byte_perm(t0, t1, 0x5140), rr = __byte_perm(t0, t1, 0x3362);
-            const unsigned nb = __dp2a_lo(a01, bg, 0u) >> 4, ng = __dp2a_hi(a01, bg, 0u) >> 4, nr = __dp2a_lo(a01, rr, 0u) >> 4;
-            const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
-            const unsigned qb = __dp2a_lo(__byte_perm(b0 * pb, b1 * nb, 0x7632), 0x0101u, 2u);
-            const unsigned qg = __dp2a_lo(__byte_perm(b0 * pg, b1 * ng, 0x7632), 0x0101u, 2u);
-            const unsigned qr = __dp2a_lo(__byte_perm(b0 * pr, b1 * nr, 0x7632), 0x0101u, 2u);
-            store_at(o0, oi, *reinterpret_cast<const float*>(divb + (qb & 0x3FCu)));
-            store_at(o1, oi, *reinterpret_cast<const float*>(divb + (qg & 0x3FCu)));
-            store_at(o2, oi, *reinterpret_cast<const float*>(divb + (qr & 0x3FCu)));
-            pb = nb; pg = ng; pr = nr; have = rt.y;
-        }
-    } else if (ry0 >= 0 && ry0 + RPT <= a.new_h) {         // no padding rows in this thread's strip (warp-uniform)
-#pragma unroll 4
-        for (int i = 0; i < RPT; ++i, oi += a.LW) {
-            const int4 rt = s_rowtap[j0 + i];
-            float v0, v1, v2;
-            resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
-            store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
-        }
+    const bool full = (ry0 >= 0) && (ry0 + RPT <= a.new_h) && (n_out == RPT);      // warp-uniform
+    if (!AREA && VTI_K1_HSHARE && full) {
+        resize_strip<LW_T, false>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, RPT, pad);
+    } else if (!AREA && VTI_K1_HSHARE && VTI_K1_PADROWS) {
+        resize_strip<LW_T, true>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, n_out, pad);
     } else {
-        for (int i = 0; i < RPT; ++i, oi += a.LW) {
-            const int ry = ry0 + i;
+        for (int i = 0; i < n_out; ++i, oi += LW) {
+            const int4 rt = s_rowtap[j0 + i];
             float v0 = pad, v1 = pad, v2 = pad;
-            if (ry >= 0 && ry < a.new_h) {
-                const int4 rt = s_rowtap[j0 + i];
-                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
+            if (rt.x >= 0) {
+                const unsigned sh = (VTI_K1_MULHI && !AREA) ? 16u : 0u;
+                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z >> sh, (unsigned)rt.w >> sh, divb, v0, v1, v2);
             }
             store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
         }
@@ -568,7 +817,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                          const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,
                          const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy,
                          std::vector<int4>& hdr, std::vector<unsigned>& lut, int& pitch_u, int& rows_u, size_t& raw_words,
-                         int& lut_stride) {
+                         int& lut_stride, int& raw_pitch) {
     const vti_geometry& g = h->g;
     const int fw = h->p.frame_w, fh = h->p.frame_h;
     if (fw & 7) return false;
@@ -607,18 +856,21 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
             pitch_u = std::max(pitch_u, und_ix ? ncols : ((ncols + 7) & ~7));   // remapped footprints pack tightly
             hdr[2 * ((size_t)ty * ntx + tx) + 1] = make_int4(r_lo, c_lo, nrows, ncols);
         }
+
     lut_stride = (rows_u * pitch_u + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
+    raw_pitch = 0;
     if (!und_ix) return true;
-    // pass 2: raw boxes + remap entries (entry 0 = offset 0, weights 0: a valid cell for the padded tail)
-    lut.assign((size_t)ntx * nty * lut_stride + FT_CHUNK, 0u);      // + one spare chunk: the loop prefetches
-    for (size_t t = 0; t < (size_t)ntx * nty; ++t) {
+    // pass 2: raw boxes, then remap entries (entry 0 = offset 0, weights 0: a valid cell for the padded tail)
+    const size_t ntiles = (size_t)ntx * nty;
+    auto clampx = [&](int x) { return x < -1 ? -2 : (x > fw - 1 ? fw : x); };
+    auto clampy = [&](int y) { return y < -1 ? -2 : (y > fh - 1 ? fh : y); };
+    int bh_max = 0;
+    for (size_t t = 0; t < ntiles; ++t) {
         const int4 f = hdr[2 * t + 1];
         const int r_lo = f.x, c_lo = f.y, nrows = f.z;
         if (nrows == 0) continue;
         const int c_end = std::min(c_lo + pitch_u, fw);            // remap every staged column that exists
         int minx = INT32_MAX, miny = INT32_MAX, maxx = INT32_MIN, maxy = INT32_MIN;
-        auto clampx = [&](int x) { return x < -1 ? -2 : (x > fw - 1 ? fw : x); };
-        auto clampy = [&](int y) { return y < -1 ? -2 : (y > fh - 1 ? fh : y); };
         for (int sy = r_lo; sy < r_lo + nrows; ++sy)
             for (int sx = c_lo; sx < c_end; ++sx) {
                 const size_t i = (size_t)sy * fw + sx;
@@ -631,23 +883,77 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
         const int bw = bx1 - bx0, by0 = miny, bh = maxy + 2 - miny;
         if ((size_t)bw * bh > 16384) return false;                  // 16-bit byte offsets
         raw_words = std::max(raw_words, (size_t)bw * bh);
+        raw_pitch = std::max(raw_pitch, bw);
+        bh_max = std::max(bh_max, bh);
         hdr[2 * t] = make_int4(bx0, by0, bw, bh);
-        unsigned* L = lut.data() + t * lut_stride;
+    }
+    const int esz = VTI_K1_LUT8 ? 2 : 1;                            // words per entry
+    if (VTI_K1_FIXPITCH) {
+        if (raw_pitch <= K1_RAWP) raw_pitch = K1_RAWP;              // the pitch the kernel has as an immediate
+        if ((size_t)raw_pitch * bh_max > 16384) return false;
+        raw_words = (size_t)raw_pitch * bh_max;                     // every tile's box at the one pitch
+    }
+    lut.assign((ntiles * lut_stride + FT_CHUNK) * esz, 0u);         // + one spare chunk: the loop prefetches
+    for (size_t t = 0; t < ntiles; ++t) {
+        const int4 f = hdr[2 * t + 1], bx = hdr[2 * t];
+        const int r_lo = f.x, c_lo = f.y, nrows = f.z;
+        if (nrows == 0) continue;
+        const int bx0 = bx.x, by0 = bx.y, bw = VTI_K1_FIXPITCH ? raw_pitch : bx.z;
+        unsigned* L = lut.data() + t * lut_stride * esz;
         for (int r = 0; r < nrows; ++r)
             for (int c = 0; c < pitch_u; ++c) {
                 const int sy = r_lo + r, sx = c_lo + c;
-                unsigned e = 0u;                                    // columns past the frame: any valid cell
+                unsigned off = 0u, fx = 0u, fy = 0u;                // columns past the frame: any valid cell
                 if (sx < fw) {
                     const size_t i = (size_t)sy * fw + sx;
                     const int ix = (*und_ix)[i], iy = (*und_iy)[i];
                     const int x = clampx(ix >> 5), y = clampy(iy >> 5);
-                    const unsigned off = (unsigned)(((y - by0) * bw + (x - bx0)) * 4);
-                    e = (off << 16) | ((unsigned)(iy & 31) << 8) | (unsigned)(ix & 31);
+                    off = (unsigned)(((y - by0) * bw + (x - bx0)) * 4);
+                    fx = (unsigned)(ix & 31); fy = (unsigned)(iy & 31);
                 }
-                L[(size_t)r * pitch_u + c] = e;
+                const size_t e = (size_t)r * pitch_u + c;
+                if (VTI_K1_LUT8) {
+                    L[2 * e] = (off << 16) | (fx << 8) | (32u - fx);
+                    L[2 * e + 1] = (fy << 16) | (32u - fy);
+                } else {
+                    L[e] = (off << 16) | (fy << 8) | fx;
+                }
             }
     }
     return true;
+}
+
+// The one place that names every instantiation of the fast kernel: launch == 0 raises each one's dynamic
+// shared-memory limit (plan time), launch == 1 launches the one that matches the handle.
+template <bool REMAP, bool AREA, int LW_T, int RAWP_T>
+static int k1_fast_one(const K1FastArgs* f, int launch, const dim3* grid, size_t smem, cudaStream_t s) {
+    if (!launch) return vti_raise_dyn_smem((const void*)k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T>, smem);
+    k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T><<<*grid, FT_THREADS, smem, s>>>(*f);
+    return VTI_OK;
+}
+template <int LW_T>
+static int k1_fast_lw(bool remap, bool area, int rawp, const K1FastArgs* f, int launch, const dim3* grid, size_t smem,
+                      cudaStream_t s) {
+    int rc = VTI_OK;
+    const bool fixed = rawp == K1_RAWP;
+    if (!launch || (remap && area && fixed)) if ((rc = k1_fast_one<true, true, LW_T, K1_RAWP>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (remap && !area && fixed)) if ((rc = k1_fast_one<true, false, LW_T, K1_RAWP>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (remap && area && !fixed)) if ((rc = k1_fast_one<true, true, LW_T, 0>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (remap && !area && !fixed)) if ((rc = k1_fast_one<true, false, LW_T, 0>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (!remap && area)) if ((rc = k1_fast_one<false, true, LW_T, 0>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (!remap && !area)) if ((rc = k1_fast_one<false, false, LW_T, 0>(f, launch, grid, smem, s))) return rc;
+    return rc;
+}
+static int k1_fast_dispatch(vti_handle* h, const K1FastArgs* f, int launch, const dim3* grid, size_t smem,
+                            cudaStream_t s = nullptr) {
+    const bool remap = h->k1_mode == MODE_FAST_REMAP, area = h->resize_mode == 2;
+    const int LW = h->g.LW, rawp = h->k1_raw_pitch;
+    int rc = VTI_OK;
+    // imgsz 960 and 640 letterboxes (every BASELINE config) get the row pitch as a compile-time constant
+    if (VTI_K1_LWT && (!launch || LW == 960)) if ((rc = k1_fast_lw<960>(remap, area, rawp, f, launch, grid, smem, s))) return rc;
+    if (VTI_K1_LWT && (!launch || LW == 640)) if ((rc = k1_fast_lw<640>(remap, area, rawp, f, launch, grid, smem, s))) return rc;
+    if (!launch || !VTI_K1_LWT || (LW != 960 && LW != 640)) rc = k1_fast_lw<0>(remap, area, rawp, f, launch, grid, smem, s);
+    return rc;
 }
 
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
@@ -659,9 +965,9 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
     {
         std::vector<int4> hdr;
         std::vector<unsigned> lut;
-        int pitch_u = 0, rows_u = 0, lut_stride = 0;
+        int pitch_u = 0, rows_u = 0, lut_stride = 0, raw_pitch = 0;
         size_t raw_words = 0;
-        if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride)) {
+        if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride, raw_pitch)) {
             const int und_words = (rows_u * pitch_u + 4 + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
             size_t smem = ((size_t)und_words + raw_words) * 4;
             // Leave room on every SM for the post kernels that run beside K1 (two streams): at most 4 resident K1 CTAs.
@@ -671,19 +977,14 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
             if (smem <= 110 * 1024) {
                 h->k1_mode = und_ix ? MODE_FAST_REMAP : MODE_FAST_PLAIN;
                 h->k1_pitch_u = pitch_u; h->k1_rows_u = rows_u; h->k1_smem = smem;
-                h->k1_und_words = und_words; h->k1_lut_stride = lut_stride;
+                h->k1_und_words = und_words; h->k1_lut_stride = lut_stride; h->k1_raw_pitch = raw_pitch;
                 VTI_CUDA(cudaMalloc((void**)&h->d_k1_tiles, sizeof(int4) * hdr.size()));
                 VTI_CUDA(cudaMemcpy(h->d_k1_tiles, hdr.data(), sizeof(int4) * hdr.size(), cudaMemcpyHostToDevice));
                 if (und_ix) {
                     VTI_CUDA(cudaMalloc((void**)&h->d_k1_lut, sizeof(unsigned) * lut.size()));
                     VTI_CUDA(cudaMemcpy(h->d_k1_lut, lut.data(), sizeof(unsigned) * lut.size(), cudaMemcpyHostToDevice));
                 }
-                const int sm = (int)smem;
-                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-                VTI_CUDA(cudaFuncSetAttribute(k1_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-                return VTI_OK;
+                return k1_fast_dispatch(h, nullptr, 0, nullptr, smem);          // raises the shared-memory limits only
             }
         }
     }
@@ -750,18 +1051,9 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
             h->k1_mode = MODE_GATHER;
         }
     }
-    {
-        if (h->k1_mode == MODE_RAW)
-            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->k1_smem));
-        else if (h->k1_mode == MODE_GATHER)
-            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_GATHER>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
-        else
-            VTI_CUDA(cudaFuncSetAttribute(k1_letterbox_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->k1_smem));
-    }
-    return VTI_OK;
+    if (h->k1_mode == MODE_RAW) return vti_raise_dyn_smem((const void*)k1_letterbox_kernel<MODE_RAW>, h->k1_smem);
+    if (h->k1_mode == MODE_GATHER) return vti_raise_dyn_smem((const void*)k1_letterbox_kernel<MODE_GATHER>, h->k1_smem);
+    return vti_raise_dyn_smem((const void*)k1_letterbox_kernel<MODE_PLAIN>, h->k1_smem);
 }
 
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s) {
@@ -779,12 +1071,10 @@ int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cu
         f.flip = h->p.channel_flip;
         f.pitch_u = h->k1_pitch_u; f.rows_u = h->k1_rows_u;
         f.und_words = h->k1_und_words; f.lut_stride = h->k1_lut_stride;
+        f.raw_pitch = h->k1_raw_pitch;
         dim3 grid((f.LW + FTX - 1) / FTX, (f.LH + FTY - 1) / FTY, B);
-        const bool remap = h->k1_mode == MODE_FAST_REMAP, area = h->resize_mode == 2;
-        if (remap && area) k1_fast_kernel<true, true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
-        else if (remap) k1_fast_kernel<true, false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
-        else if (area) k1_fast_kernel<false, true><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
-        else k1_fast_kernel<false, false><<<grid, FT_THREADS, h->k1_smem, s>>>(f);
+        int rc = k1_fast_dispatch(h, &f, 1, &grid, h->k1_smem, s);
+        if (rc) return rc;
         h->launches++;
         VTI_CUDA(cudaGetLastError());
         return VTI_OK;

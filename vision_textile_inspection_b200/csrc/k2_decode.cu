@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_decode_kernel(const K2Args a) {
                 p0 = __shfl_sync(0xffffffffu, p0, 0);
                 if (cand) {
                     const int p = p0 + __popc(m & ((1u << lane) - 1u));
-                    s_idx[p] = i | (cls << 24);
+                    s_idx[p] = (int)((unsigned)i | ((unsigned)cls << 24));
                     s_best[p] = best;
                 }
             }
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_decode_kernel(const K2Args a) {
                 p0 = __shfl_sync(0xffffffffu, p0, 0);
                 if (cand) {
                     const int p = p0 + __popc(m & ((1u << lane) - 1u));
-                    s_idx[p] = i | (cls << 24);
+                    s_idx[p] = (int)((unsigned)i | ((unsigned)cls << 24));
                     s_best[p] = best;
                 }
             }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_decode_kernel(const K2Args a) {
             const int anchor = a.a_begin[l] + (s_idx[c] & 0xFFFFFF);
             a.cand_key[(size_t)b * a.cap_pad + slot] = ((unsigned long long)__float_as_uint(s_best[c]) << 32) |
                                                         ((unsigned long long)(0xFFFFFFu - (unsigned)anchor) << 8) |
-                                                        (unsigned)(s_idx[c] >> 24);
+                                                        ((unsigned)s_idx[c] >> 24);     // unsigned: classes >= 128 must not sign-extend
         }
     }
 }

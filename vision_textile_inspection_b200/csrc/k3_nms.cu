@@ -416,9 +416,7 @@ int vti_k3_cap_pad(int cap) {
 }
 
 int vti_k3_prepare(int cap) {
-    VTI_CUDA(cudaFuncSetAttribute(k3_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)vti_k3_smem_bytes(cap)));
-    return VTI_OK;
+    return vti_raise_dyn_smem((const void*)k3_nms_kernel, vti_k3_smem_bytes(cap));
 }
 
 int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, int all_dets, cudaStream_t s) {

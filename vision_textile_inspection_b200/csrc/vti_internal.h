@@ -44,6 +44,7 @@ struct vti_handle {
     int k1_mode, k1_pitch_u, k1_rows_u;            // staging mode + shared footprint buffer shape (k1 plan)
     size_t k1_smem;
     int k1_und_words, k1_lut_stride;               // fast path: footprint buffer words, table entries per tile
+    int k1_raw_pitch;                              // fast remap path: words per row of the staged raw box
     int4* d_k1_tiles;                              // per-tile headers (fast path) / raw bounding boxes (MODE_RAW)
     unsigned* d_k1_lut;                            // per-tile pre-resolved remap entries (fast path, undistort)
     // ---- measurement tables (device)
@@ -83,6 +84,8 @@ void vti_set_error(const std::string& s);
         }                                                                                          \
     } while (0)
 
+// raises (never lowers) a kernel function's dynamic shared-memory limit on the current device
+int vti_raise_dyn_smem(const void* func, size_t bytes);
 // kernel launchers (each returns VTI_OK / VTI_ECUDA)
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
                 const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,

@@ -93,7 +93,12 @@ class EngineConfig:
         p.conf, p.iou = self.conf, self.iou
         p.iou_threshold = float(self.iou)          # the Python float torchvision.ops.nms receives (a C++ double)
         p.K[:] = np.asarray(self.K, np.float64).reshape(9).tolist()
-        p.dist[:] = np.asarray(self.dist, np.float64).reshape(-1)[:5].tolist()
+        d = np.asarray(self.dist, np.float64).reshape(-1)
+        if d.size > 5 and np.any(d[5:] != 0.0):
+            raise ValueError("EngineConfig.dist: only the 5-coefficient model (k1, k2, p1, p2, k3) is implemented; "
+                             f"got {d.size} coefficients with non-zero higher terms")
+        d = np.concatenate([d[:5], np.zeros(max(0, 5 - d.size))])
+        p.dist[:] = d.tolist()
         p.R[:] = np.asarray(self.R, np.float64).reshape(9).tolist()
         p.t[:] = np.asarray(self.t, np.float64).reshape(3).tolist()
         return p

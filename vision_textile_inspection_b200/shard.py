@@ -65,15 +65,24 @@ class PeerGather:
     all-gather moves W times more bytes than needed and its NCCL kernel takes SMs from K1.  Here every rank owns a
     symmetric-memory buffer [slots][W][bytes]; a rank pushes its packed records into ROOT's copy of slot s, row
     `rank`, with one device-to-device copy through the peer mapping (copy engine over NVLink / NVSwitch), then raises
-    a signal that root's stream waits on.  The signal handshake is also the flow control: a rank cannot raise signal
-    s + 1 before root has consumed signal s, so with two slots a row is never overwritten while root may still read it.
+    a signal that root's stream waits on.
+
+    Flow control.  put_signal(n + 1) completes only once root's wait_signal(n) has consumed signal n, and a rank's
+    copy of step n + k is ordered (same stream) after its put_signal(n + k - 1).  Root's wait_signal(n) precedes its
+    READ of slot n, so with two slots the copy of step n + 2 could land in the row root is still reading.  With THREE
+    slots (step n uses slot n % 3) the copy of step n + 3 is ordered after root consumed signal n + 1, which root's
+    stream issues after its read of slot n -- provided root reads on the SAME stream that issued the waits, which is
+    what push()/consume() do.  tests/test_peer_gather.py reads the slot every step on 2 GPUs.
     """
 
-    def __init__(self, nbytes: int, device, group=None, root: int = 0, slots: int = 2):
+    def __init__(self, nbytes: int, device, group=None, root: int = 0, slots: int = 3):
         import torch.distributed._symmetric_memory as symm
+        if slots < 3:
+            raise ValueError("PeerGather needs >= 3 slots (see the flow-control note in the class docstring)")
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world, self.root, self.slots = dist.get_rank(group), dist.get_world_size(group), root, slots
         self.nbytes = nbytes
+        self.step = 0
         self.buf = symm.empty((slots, self.world, nbytes), dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
@@ -81,8 +90,11 @@ class PeerGather:
         torch.cuda.synchronize(device)
         self.hdl.barrier()
 
-    def push(self, packed: torch.Tensor, slot: int) -> None:
-        """Enqueue, on the current stream, this rank's copy into root's slot and the signal exchange."""
+    def push(self, packed: torch.Tensor, slot: int | None = None) -> int:
+        """Enqueue, on the current stream, this rank's copy into root's slot and the signal exchange.  Every rank must
+        call push() the same number of times, from one stream; returns the slot used (step % slots)."""
+        slot = self.step % self.slots if slot is None else slot
+        self.step += 1
         self.root_buf[slot, self.rank].copy_(packed.view(-1))
         if self.rank != self.root:
             self.hdl.put_signal(self.root, channel=self.rank)
@@ -90,7 +102,18 @@ class PeerGather:
             for r in range(self.world):
                 if r != self.root:
                     self.hdl.wait_signal(r, channel=r)
+        return slot
 
     def gathered(self, slot: int) -> torch.Tensor:
-        """Root only: (W, bytes) view of a slot; unpack_packed() gives the typed views in global frame order."""
+        """Root only: (W, bytes) view of a slot; unpack_packed() gives the typed views in global frame order.  Read it
+        on the stream push() ran on, before the push() two steps later (or use consume())."""
         return self.buf[slot]
+
+    def consume(self, slot: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Root only: copy a gathered slot out on the current stream (the one push() ran on), so that the slot may be
+        reused; returns the (W, bytes) copy."""
+        src = self.buf[slot]
+        if out is None:
+            out = torch.empty_like(src)
+        out.copy_(src)
+        return out
