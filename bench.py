@@ -7,7 +7,12 @@ A step = one pass of the hot path (K1 undistort+letterbox, K2 decode/filter, K3 
 over one batch of synthetic frames + planted head tensors already resident in HBM.  N=1 workload = BASELINE.json
 configs[1] (64 x 1280x720, undistort on).  For N>1 the driver launches one rank per GPU with torchrun; every rank runs
 its own batch (weak scaling, no data-path collective) and pushes its compact per-defect records to rank 0 each step
-through NVLink peer memory (shard.PeerGather; --gather nccl = an all-gather of the same buffers).
+through NVLink peer memory (shard.PeerGather; --gather nccl = an all-gather of the same buffers).  At N>1 the line also
+carries `cfg5_sharded`: BASELINE.json configs[4], 256 synthetic 4K frames SPLIT over the ranks (shard.shard_range,
+strong scaling), resident and end to end, records gathered -- beside the weak-scaled cfg2 headline.
+The CPU arm (cpu_baseline / --impl reference) runs the reference's OWN measurement.py (staged by
+baseline/stage_reference.py into baseline/_ref/) behind the Ultralytics restatement on real cv2/torch/torchvision
+operators; without the staged copy it falls back to the measure-stage port and says kind "port".
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -49,13 +54,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def stage_bytes(cfg, n_det_mean: float):
-    """Algorithmic bytes per FRAME and stage (fused path, no mask export)."""
+def stage_bytes(cfg, n_det_mean: float, n_cand_mean: float | None = None):
+    """Algorithmic bytes per FRAME and stage (fused path, no mask export).  With n_cand_mean, K2 is what the
+    kernel MUST read -- the class planes of every anchor plus the 64 box logits of each confidence-passing anchor, and
+    its key + box outputs -- instead of SURVEY's whole-head figure 4 A (64 + nc), which the kernel never touches (ncu:
+    19 MB per 64 frames against 181 MB), so that a K2 "fraction of roofline" can never be flattered by bytes not moved."""
     h, w, LH, LW = cfg.frame_h, cfg.frame_w, cfg.LH, cfg.LW
     ph, pw, A = LH // 4, LW // 4, cfg.anchors
     return {
         "K1": 3 * h * w + 12 * LH * LW,
-        "K2": 4 * A * (64 + cfg.nc),
+        "K2": 4 * A * (64 + cfg.nc) if n_cand_mean is None else 4 * A * cfg.nc + n_cand_mean * (64 * 4 + 8 + 16),
         "K3": n_det_mean * (32 + 4 + 2) * 4,
         "K4": 128 * ph * pw,
         "K5": 64 * n_det_mean,
@@ -116,7 +124,7 @@ def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 3, single_thread
     and the measure-stage port (oracle/), frame by frame like the reference (batch 1, measurement.py:208-211)."""
     import cv2
     import torch
-    from oracle import cv_fixed, measure_port, ultra_ref
+    from oracle import cv_fixed, measure_port, ref_verbatim, ultra_ref
     ncpu = os.cpu_count() or 1
     if set_threads:
         if torch.get_num_threads() < ncpu:      # torchrun exports OMP_NUM_THREADS=1: the CPU arm gets every host thread
@@ -129,12 +137,18 @@ def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 3, single_thread
                                     R=measure_port.rodrigues(ex["rvec"]), t=np.array(ex["tvec"]), variant=cfg.variant,
                                     roi=cfg.roi(), max_px_distance=250 if cfg.variant == 0 else 150)
 
+    app = None
+    if ref_verbatim.available():           # the reference's own process_frame (measurement.py / check_stitch_distance.py)
+        _, app = ref_verbatim.make_app(cfg.variant, mc.K, mc.dist, mc.R, mc.t, roi=cfg.roi() if cfg.variant == 0 else None)
+
     def one(i):
         f = batch["frames"][i]
         ultra_ref.preprocess([f], cfg.imgsz, undistort=(K, dist) if cfg.undistort else None)
         r = ultra_ref.postprocess([l[i:i + 1] for l in batch["levels"]], batch["coef"][i:i + 1],
                                   batch["proto"][i:i + 1], (cfg.frame_h, cfg.frame_w), cfg.conf, cfg.iou, cfg.max_det,
                                   cfg.nc)[0]
+        if app is not None:
+            return ref_verbatim.run_frame(app, f, r)
         return measure_port.measure_frame(r.boxes.cls.numpy(), r.boxes.xyxy.numpy(), r.masks.data.numpy(),
                                           cfg.frame_h, cfg.frame_w, mc)
     nb = batch["frames"].shape[0]
@@ -147,7 +161,8 @@ def cpu_reference(cfg, batch, calib, n_frames: int, warm: int = 3, single_thread
         one(i % nb)
         per.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
-    cores = {"os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cv2_threads": cv2.getNumThreads(),
+    cores = {"measure_stage": "verbatim reference (baseline/_ref)" if app is not None else "port (oracle/measure_port.py)",
+             "os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cv2_threads": cv2.getNumThreads(),
              "ms_per_frame_median": 1e3 * float(np.median(per)), "ms_per_frame_p10": 1e3 * float(np.percentile(per, 10)),
              "ms_per_frame_p90": 1e3 * float(np.percentile(per, 90))}
     if single_thread_frames:
@@ -197,6 +212,16 @@ def cpu_reference_parallel(cfg_key, batch, calib, frames_per_worker: int, worker
     return workers * frames_per_worker / max(ts), max(ts)
 
 
+def cpu_kind() -> tuple[str, str]:
+    """("reference", ...) when the reference's own measure-stage code is staged and runs, else ("port", ...)."""
+    from oracle import ref_verbatim
+    if ref_verbatim.available():
+        return "reference", ("pre/post = the Ultralytics calls restated on the real cv2 / torch / torchvision operators "
+                             "(ultralytics itself is not installable offline), measure = the reference's own "
+                             "process_frame run verbatim from " + os.path.relpath(ref_verbatim.REF, ROOT))
+    return "port", "cv2+torch+torchvision operators + measure-stage port (no staged reference copy found)"
+
+
 def run_reference(args, cfg, rank, world):
     """--impl reference: the CPU path alone on every host core (frame-parallel, one single-threaded process per core);
     a step is a bounded sample of the workload: `workers` x 2 frames."""
@@ -212,15 +237,16 @@ def run_reference(args, cfg, rank, world):
     fps, secs = cpu_reference_parallel(args.config, batch, calib, fpw * max(args.steps, 1), workers)
     seq_fps, _, cores = cpu_reference(cfg, batch, calib, 6, warm=1)       # the reference as it runs: one process
     n_sample = workers * fpw
+    kind, kind_txt = cpu_kind()
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg.name, "frames_per_step": n_sample, "frame": [cfg.frame_w, cfg.frame_h],
                    "net_in": [cfg.LW, cfg.LH]},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": workers, "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": workers, "kind": kind,
                          "sample": f"{n_sample} frames/step of {cfg.name}: {workers} single-threaded processes x {fpw} "
-                                   f"frames, cv2+torch+torchvision operators + measure-stage port (frame-parallel; the "
+                                   f"frames, {kind_txt} (frame-parallel; the "
                                    f"reference's own one-process loop with library threading does {seq_fps:.2f} frames/s, "
                                    f"threads={cores})"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -560,10 +586,10 @@ def run_b200(args, cfg, rank, world, local_rank):
         fps, dt, cores = cpu_reference(cfg, batch, calib, n_cpu, single_thread_frames=6)
         workers = os.cpu_count() or 1
         par_fps, par_s = cpu_reference_parallel(args.config, batch, calib, 4, workers)
-        cpu = {"value": par_fps, "unit": UNIT, "cores": workers, "kind": "port",
+        kind, kind_txt = cpu_kind()
+        cpu = {"value": par_fps, "unit": UNIT, "cores": workers, "kind": kind,
                "sample": f"frame-parallel: {workers} single-threaded processes x 4 frames of {cfg.name} in {par_s:.1f}s "
-                         f"(batch-1 loop per process: cv2.undistort+LetterBox, torch decode/torchvision nms/process_mask, "
-                         f"measure-stage port); the reference's own one-process loop with library threading: "
+                         f"(batch-1 loop per process: {kind_txt}); the reference's own one-process loop with library threading: "
                          f"{fps:.2f} frames/s over {n_cpu} frames in {dt:.1f}s; threads={cores}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

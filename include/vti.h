@@ -49,6 +49,9 @@ extern "C" {
 #define VTI_F_FINAL 32u      /* envelope-proximity filter (measurement.py:409-430) */
 #define VTI_F_HAS_WIDTH 64u
 #define VTI_F_HAS_DIST 128u
+#define VTI_F_LB_MASK 256u   /* the letterbox-resolution mask (Results.masks.data) has at least one pixel set */
+#define VTI_F_DROPPED 512u   /* mask_variant 1 only: empty mask, removed by Ultralytics' construct_result (not routed,
+                                not counted in vti_frame_result.n_det; hosts skip these records) */
 
 /* frame_result.status */
 #define VTI_ST_OK 0
@@ -81,6 +84,10 @@ typedef struct vti_params {
     double t[3];                  /* tvec, metres */
     double iou_threshold;         /* predict(iou=...) as the DOUBLE torchvision.ops.nms compares against
                                      (`ovr > iou_threshold`, ovr float32); 0 = use (double)iou */
+    int32_t mask_variant;         /* SURVEY 8a U6.  0 = "A" (Ultralytics <= 8.0.x, the north-star wording):
+                                     sigmoid -> crop -> bilinear x4 -> > 0.5.  1 = "B" (newer releases): no sigmoid,
+                                     crop, bilinear x4, > 0.0, and detections whose mask is empty are dropped */
+    int32_t reserved0;
 } vti_params;
 
 typedef struct vti_geometry {
@@ -111,12 +118,15 @@ typedef struct vti_det {
     double width_mm;              /* NaN if not computed */
     double edge_y;                /* median envelope row near cx */
     double dist_mm;               /* NaN if not computed */
-    double reserved;              /* pads the record to 160 bytes */
+    double area_mm2;              /* area of the frame-resolution bitmap on the fabric plane: m00 x the area of one
+                                     pixel at the centroid, |dP/du x dP/dv| by central differences of the
+                                     pixel -> world projection (north-star "area"; the reference has no such
+                                     output, oracle/measure_port.py defect_area_mm2 is the spec).  NaN if no mask */
 } vti_det;
 
 typedef struct vti_frame_result {
     int32_t status;
-    int32_t n_det, n_cand;
+    int32_t n_det, n_cand;        /* n_det: kept detections (minus VTI_F_DROPPED ones); n_cand: confidence-passing anchors */
     int32_t n_stitch, n_fabric;   /* routed stitch boxes / fabric masks after the ROI filter */
     int32_t n_dist, n_width;      /* len(per_dists), len(all_widths) */
     int32_t env_valid;            /* frame columns with fabric */

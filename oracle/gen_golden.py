@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 from oracle import cv_fixed, measure_port, ref_verbatim, ultra_ref  # noqa: E402
 from vision_textile_inspection_b200 import synth  # noqa: E402
 
-SCENES = [("native", 0), ("native", 1), ("native", 2), ("cfg1", 1000), ("cfg2", 2000), ("cfg2", 2001),
-          ("cfg3", 3000), ("cfg3", 3001), ("cfg4", 4000)]
+SCENES = [("native", 0), ("native", 1), ("native", 2), ("cfg1", 1000), ("cfg1", 1001), ("cfg1", 1002), ("cfg2", 2000),
+          ("cfg2", 2001), ("cfg3", 3000), ("cfg3", 3001), ("cfg4", 4000), ("cfg5", 5000), ("cfg5", 5001)]
 SEQUENCE = ("native", list(range(10, 22)))
 
 

@@ -88,6 +88,25 @@ def pixel_to_world(u, v, c: MeasureConfig):
     return c.R.T.dot((-c.d_c / den) * ray - c.t)
 
 
+def defect_area_mm2(bitmap: np.ndarray, c: MeasureConfig):
+    """Spec of vti_det.area_mm2 (the north-star's "area"; the reference itself never outputs one -- it only uses m00 as
+    a centroid denominator, measurement.py:304-307 -- so this numpy function IS the definition, not a restatement).
+
+    Area of the frame-resolution bitmap on the fabric plane: (number of set pixels) x (plane area of one pixel at the
+    bitmap's centroid), the latter as |dP/du x dP/dv| by central differences (+-0.5 px) of the reference's own
+    pixel -> world projection (pixel_to_world above = measurement.py:50-65).  mm^2; None if the bitmap is empty."""
+    M = cv2.moments(bitmap)
+    if M["m00"] <= 0:
+        return None
+    cx, cy = M["m10"] / M["m00"], M["m01"] / M["m00"]
+    pts = [pixel_to_world(cx - 0.5, cy, c), pixel_to_world(cx + 0.5, cy, c),
+           pixel_to_world(cx, cy - 0.5, c), pixel_to_world(cx, cy + 0.5, c)]
+    if any(p is None for p in pts):
+        return None
+    du, dv = pts[1] - pts[0], pts[3] - pts[2]
+    return float(M["m00"]) * float(np.linalg.norm(np.cross(du, dv))) * 1e6
+
+
 def instance_bitmap(mask_lb: np.ndarray, h: int, w: int):
     """measurement.py:70-86 -- nearest-resize the WHOLE letterboxed mask (pad rows included) to the frame."""
     arr = np.asarray(mask_lb)

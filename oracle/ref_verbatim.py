@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the reference's own measure-stage modules VERBATIM from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- loads the reference's own measure-stage modules VERBATIM.
 
-Works only in the build container (the GPU box has no /root/reference); used by oracle/gen_golden.py to produce
-tests/golden/*.json and by tests/test_oracle_measure.py (skipped when /root/reference is absent) to pin
-oracle/measure_port.py against the reference itself.  Nothing is copied: the modules are imported where they lie.
+Source: /root/reference in the build container; on the GPU box (which has no /root/reference) the copy that
+baseline/stage_reference.py staged into baseline/_ref/ (git-ignored, shipped by gpurun).  Used by oracle/gen_golden.py
+to produce tests/golden/*.json, by tests/test_oracle_measure.py to pin oracle/measure_port.py against the reference
+itself, by tests/test_app.py to run the reference's own process_frame with the B200 predictor plugged in
+(INTEGRATION.md 2), and by bench.py's CPU arm (kind "reference").  The modules are imported where they lie.
 
 Recipe: stub `ultralytics` (measurement.py:9) and `serial` (config.py:7 -> hardware_utils.py:1), set
 dummy DB_* variables (config.py:132-133 raises without them), then build StitchMeasurementApp with __new__ so that
@@ -20,7 +22,8 @@ from collections import deque
 
 import numpy as np
 
-REF = "/root/reference"
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REF = "/root/reference" if os.path.isfile("/root/reference/measurement.py") else _STAGED
 
 
 def available() -> bool:

@@ -121,11 +121,22 @@ def crop_mask(masks: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
     return masks * ((r >= x1) * (r < x2) * (c >= y1) * (c < y2))
 
 
-def process_mask(proto: torch.Tensor, coef: torch.Tensor, boxes_lb: torch.Tensor, shape) -> torch.Tensor:
-    """ops.process_mask(upsample=True), variant A [U6].  proto (32,ph,pw), coef (N,32), boxes (N,4) letterbox px."""
+def process_mask(proto: torch.Tensor, coef: torch.Tensor, boxes_lb: torch.Tensor, shape, variant: str = "A",
+                 return_soft: bool = False):
+    """ops.process_mask(upsample=True) [U6].  proto (32,ph,pw), coef (N,32), boxes (N,4) letterbox px.
+
+    variant "A" (Ultralytics <= 8.0.x, the north-star wording): sigmoid -> crop -> bilinear x4 -> > 0.5.
+    variant "B" (newer releases): NO sigmoid, crop, bilinear x4, > 0.0 (the caller additionally drops
+    detections whose mask is empty: see postprocess(mask_variant="B")).  The crop is the float-compare crop_mask in
+    both (the rounded-slice crop newer releases use for n < 50 on CPU is not reproduced: SURVEY 8a marks it optional).
+    return_soft: also return the float map before the threshold (tests check that a pixel that differs from the CUDA
+    path sits on the threshold to within float rounding)."""
     c, mh, mw = proto.shape
     ih, iw = shape
-    masks = (coef @ proto.float().view(c, -1)).sigmoid().view(-1, mh, mw)
+    masks = (coef @ proto.float().view(c, -1))
+    if variant == "A":
+        masks = masks.sigmoid()
+    masks = masks.view(-1, mh, mw)
     db = boxes_lb.clone()
     db[:, 0] *= mw / iw
     db[:, 2] *= mw / iw
@@ -136,7 +147,9 @@ def process_mask(proto: torch.Tensor, coef: torch.Tensor, boxes_lb: torch.Tensor
         masks = Fnn.interpolate(masks[None], shape, mode="bilinear", align_corners=False)[0]
     else:
         masks = masks.new_zeros((0, ih, iw))
-    return masks.gt_(0.5)
+    soft = masks.clone() if return_soft else None
+    hard = masks.gt_(0.5 if variant == "A" else 0.0)
+    return (hard, soft) if return_soft else hard
 
 
 def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape) -> torch.Tensor:
@@ -175,8 +188,11 @@ class RefResults:
         self.keep_anchor = anchors
 
 
-def postprocess(levels, coef, proto, frame_hw, conf_thres, iou_thres, max_det, nc, with_masks=True):
-    """U3..U7 for a batch.  levels: list of (B,64+nc,Hl,Wl); coef (B,32,A); proto (B,32,ph,pw).  -> [RefResults]"""
+def postprocess(levels, coef, proto, frame_hw, conf_thres, iou_thres, max_det, nc, with_masks=True, mask_variant="A",
+                return_soft=False):
+    """U3..U7 for a batch.  levels: list of (B,64+nc,Hl,Wl); coef (B,32,A); proto (B,32,ph,pw).  -> [RefResults]
+    mask_variant "B": newer-Ultralytics masks, and detections whose mask is empty are dropped (construct_result's
+    `keep = masks.amax((-2, -1)) > 0`)."""
     levels = [torch.as_tensor(l, dtype=torch.float32) for l in levels]
     coef = torch.as_tensor(coef, dtype=torch.float32)
     proto = torch.as_tensor(proto, dtype=torch.float32)
@@ -184,7 +200,17 @@ def postprocess(levels, coef, proto, frame_hw, conf_thres, iou_thres, max_det, n
     pred = torch.cat((decode(levels, nc), coef), 1)
     res = []
     for b, (x, anchors) in enumerate(non_max_suppression(pred, conf_thres, iou_thres, max_det, nc)):
-        masks = process_mask(proto[b], x[:, 6:], x[:, :4], (LH, LW)) if with_masks else None
+        masks = soft = None
+        if with_masks:
+            masks = process_mask(proto[b], x[:, 6:], x[:, :4], (LH, LW), mask_variant, return_soft)
+            if return_soft:
+                masks, soft = masks
+            if mask_variant == "B":
+                keep = masks.amax((-2, -1)) > 0
+                x, anchors, masks = x[keep], anchors[keep], masks[keep]
+                soft = soft[keep] if soft is not None else None
         xyxy = scale_boxes((LH, LW), x[:, :4], frame_hw)
-        res.append(RefResults(xyxy, x[:, 4], x[:, 5], masks, x[:, :4].clone(), anchors))
+        r = RefResults(xyxy, x[:, 4], x[:, 5], masks, x[:, :4].clone(), anchors)
+        r.soft = soft
+        res.append(r)
     return res

@@ -24,13 +24,13 @@ def measure_config(cfg, calib) -> measure_port.MeasureConfig:
         roi=cfg.roi(), max_px_distance=250 if cfg.variant == 0 else 150)
 
 
-def oracle_scene(cfg, seed, calib, with_masks=True):
+def oracle_scene(cfg, seed, calib, with_masks=True, return_soft=False, mask_variant="A"):
     """Oracle post + measure for one seeded frame.  Returns (head dict, RefResults, measure dict)."""
     sc = synth.make_scene(cfg, seed)
     hd = synth.planted_head(cfg, seed, sc)
     res = ultra_ref.postprocess([l[None] for l in hd["levels"]], hd["coef"][None], hd["proto"][None],
                                 (cfg.frame_h, cfg.frame_w), cfg.conf, cfg.iou, cfg.max_det, cfg.nc,
-                                with_masks=with_masks)[0]
+                                with_masks=with_masks, return_soft=return_soft, mask_variant=mask_variant)[0]
     m = None
     if with_masks:
         m = measure_port.measure_frame(res.boxes.cls.numpy(), res.boxes.xyxy.numpy(), res.masks.data.numpy(),

@@ -19,6 +19,25 @@ from vision_textile_inspection_b200.engine import EngineConfig, InspectionEngine
 pytestmark = pytest.mark.gpu
 MM_RTOL = 1e-3          # 0.1 %  (north star); observed differences are ~1e-12
 IOU_BAR = 0.999
+TIE_EPS = 1e-5          # a mask pixel may differ from torch only if torch's value is this close to the threshold
+FLIPS = __import__("collections").defaultdict(lambda: dict(instances=0, pixels=0, flipped_instances=0, flipped_pixels=0,
+                                                           max_margin=0.0))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _report_mask_flips():
+    """Prints, per config, how many instances / pixels differed from torch and the largest distance of such a pixel
+    from the threshold (run with -s or read gpurun_out/mask_flips.json)."""
+    yield
+    if FLIPS:
+        rep = {k: dict(v) for k, v in FLIPS.items()}
+        print("\nmask flips vs torch (per config):", json.dumps(rep))
+        try:
+            os.makedirs(os.path.join(helpers.ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(helpers.ROOT, "gpurun_out", "mask_flips.json"), "w") as f:
+                json.dump(rep, f, indent=1)
+        except OSError:
+            pass
 
 
 def dev(a):
@@ -68,8 +87,8 @@ def test_k1_odd_shapes(h, w, imgsz):
 
 
 # ---------------------------------------------------------------------------------------------------- post + measure
-POST_CASES = [("native", [0, 1, 2]), ("cfg1", [1000]), ("cfg2", [2000, 2001, 2002]), ("cfg3", [3000, 3001]),
-              ("cfg4", [4000, 4001])]
+POST_CASES = [("native", [0, 1, 2]), ("cfg1", [1000, 1001, 1002]), ("cfg2", [2000, 2001, 2002]), ("cfg3", [3000, 3001]),
+              ("cfg4", [4000, 4001]), ("cfg5", [5000, 5001])]      # cfg5 = 4K frames: largest multiplicity LUTs / sums
 
 
 def run_gpu(cfg, seeds, export_masks=True):
@@ -123,29 +142,42 @@ def test_masks_and_measurements(name, seeds, calib):
     mc = helpers.measure_config(cfg, calib)
     for b, seed in enumerate(seeds):
         n = int(counts[b])
-        _, res, m = helpers.oracle_scene(cfg, seed, calib)
+        _, res, m = helpers.oracle_scene(cfg, seed, calib, return_soft=True)
         ref_masks = res.masks.data.numpy() > 0
+        soft = res.soft.numpy()
         got_masks = eng.unpack_masks(masks, b, n).cpu().numpy() > 0
         assert got_masks.shape == ref_masks.shape
         d = dets[b, :n]
-        n_small = 0
         for k in range(n):
             iou_lb = _iou(got_masks[k], ref_masks[k])
             iou_fr = _iou(got_masks[k][my][:, mx], ref_masks[k][my][:, mx])
-            if ref_masks[k].sum() < 1000:          # IoU of a handful of pixels: allow one boundary pixel
-                n_small += 1
-                assert np.logical_xor(got_masks[k], ref_masks[k]).sum() <= 1, (k, iou_lb)
-            else:
+            diff = np.logical_xor(got_masks[k], ref_masks[k])
+            FLIPS[name]["instances"] += 1
+            FLIPS[name]["pixels"] += int(ref_masks[k].sum())
+            if diff.any():
+                # a pixel may differ from torch ONLY where torch's own value sits on the threshold to within float
+                # rounding (the kernel sums the 32 products and interpolates in another order): |value - 0.5| <= 1e-5
+                margin = np.abs(soft[k][diff] - 0.5)
+                FLIPS[name]["flipped_instances"] += 1
+                FLIPS[name]["flipped_pixels"] += int(diff.sum())
+                FLIPS[name]["max_margin"] = max(FLIPS[name]["max_margin"], float(margin.max()))
+                assert margin.max() <= TIE_EPS, (k, int(diff.sum()), float(margin.max()))
+            if ref_masks[k].sum() >= 1000:          # the north-star bar, literally, wherever 0.999 is resolvable
                 assert iou_lb >= IOU_BAR and iou_fr >= IOU_BAR, (k, iou_lb, iou_fr)
+            else:                                   # < 1000 px: one pixel is already > 0.1 % -- only threshold ties
+                assert diff.sum() <= 1, (k, iou_lb)
             # statistics are EXACT given the mask the GPU produced (cv2.resize NEAREST + cv2.moments on it)
             bm = measure_port.instance_bitmap(got_masks[k].astype(np.float32), h, w)
             if bm is None:
-                assert d["m00"][k] == 0 and not (d["flags"][k] & _lib.F_HAS_MASK)
+                assert d["m00"][k] == 0 and not (d["flags"][k] & _lib.F_HAS_MASK) and np.isnan(d["area_mm2"][k])
             else:
                 M = cv2.moments(bm)
                 cols = np.where(bm.any(axis=0))[0]
                 assert (d["m00"][k], d["m10"][k], d["m01"][k]) == (int(M["m00"]), int(M["m10"]), int(M["m01"]))
                 assert (d["col_min"][k], d["col_max"][k]) == (cols.min(), cols.max())
+                # defect area on the fabric plane (north-star "area"): numpy spec in oracle/measure_port.py
+                area = measure_port.defect_area_mm2(bm, mc)
+                assert area is not None and abs(d["area_mm2"][k] - area) <= 1e-9 * area, (k, d["area_mm2"][k], area)
         # the measure stage run by the oracle on the GPU's own masks must agree on every decision and to ~1 ulp
         mg = measure_port.measure_frame(d["cls"], d["box_frame"], got_masks.astype(np.float32), h, w, mc)
         r = results[b]
@@ -181,6 +213,47 @@ def test_masks_and_measurements(name, seeds, calib):
                     assert np.isnan(r[key])
                 else:
                     assert abs(r[key] - ref) <= MM_RTOL * ref, (key, r[key], ref)
+
+
+@pytest.mark.parametrize("name,seeds", [("native", [0, 1]), ("cfg2", [2000]), ("cfg4", [4000])])
+def test_mask_variant_b(name, seeds, calib):
+    """Newer-Ultralytics masks (SURVEY 8a U6 variant B): logits, no sigmoid, > 0.0, empty-mask detections dropped.
+    Oracle: ultra_ref.process_mask(variant="B") on the real torch operators."""
+    cfg = synth.CONFIGS[name]
+    heads = [synth.planted_head(cfg, s) for s in seeds]
+    eng = make_engine(cfg, len(seeds), mask_variant=1)
+    lv = [dev(np.stack([h["levels"][l] for h in heads])) for l in range(3)]
+    dets, counts, results, masks = eng.post_measure(lv[0], lv[1], lv[2], dev(np.stack([h["coef"] for h in heads])),
+                                                    dev(np.stack([h["proto"] for h in heads])), export_masks=True)
+    torch.cuda.synchronize()
+    dets, counts, results = eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results)
+    mc = helpers.measure_config(cfg, calib)
+    for b, seed in enumerate(seeds):
+        n = int(counts[b])
+        d = dets[b, :n]
+        _, res, m = helpers.oracle_scene(cfg, seed, calib, return_soft=True, mask_variant="B")
+        kept = np.array([not (f & _lib.F_DROPPED) for f in d["flags"]], bool)
+        assert np.array_equal(d["anchor"][kept], res.keep_anchor.numpy())        # the same detections survive the drop
+        assert results["n_det"][b] == kept.sum() == res.boxes.cls.shape[0]
+        got = (eng.unpack_masks(masks, b, n).cpu().numpy() > 0)[kept]
+        ref, soft = res.masks.data.numpy() > 0, res.soft.numpy()
+        for k in range(ref.shape[0]):
+            diff = np.logical_xor(got[k], ref[k])
+            if diff.any():                # only on threshold ties of torch's own logit map (|logit| within rounding of 0)
+                assert np.abs(soft[k][diff]).max() <= 1e-4, (k, int(diff.sum()), float(np.abs(soft[k][diff]).max()))
+            if ref[k].sum() >= 1000:
+                assert _iou(got[k], ref[k]) >= IOU_BAR
+            else:
+                assert diff.sum() <= 1
+        r = results[b]
+        assert r["status"] == {"ok": 0, "no_fabric": 2, "no_stitch": 3}[m["status"]]
+        if m["status"] == "ok":
+            assert (r["n_dist"], r["n_width"]) == (m["n_dist"], m["n_width"])
+            for key, refv in (("avg_dist", m["avg_dist"]), ("avg_width", m["avg_width"])):
+                if refv is None:
+                    assert np.isnan(r[key])
+                else:
+                    assert abs(r[key] - refv) <= MM_RTOL * refv
 
 
 def test_against_verbatim_reference_goldens(calib):

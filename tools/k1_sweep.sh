@@ -9,11 +9,11 @@ build() {  # name flags...
   echo built $name
 }
 rm -rf tools/_variants; mkdir -p tools/_variants
-build A_lwt_nostage2_nodivfma -DVTI_K1_LWT=1 -DVTI_K1_STAGE2=0 -DVTI_K1_DIVFMA=0
-build B_lwt_nostage2 -DVTI_K1_LWT=1 -DVTI_K1_STAGE2=0
-build C_lwt -DVTI_K1_LWT=1
-build D_A_t128 -DVTI_K1_LWT=1 -DVTI_K1_STAGE2=0 -DVTI_K1_DIVFMA=0 -DVTI_FT_THREADS=128 -DVTI_FT_MINB=8
-build E_A_t128_ty16 -DVTI_K1_LWT=1 -DVTI_K1_STAGE2=0 -DVTI_K1_DIVFMA=0 -DVTI_FT_THREADS=128 -DVTI_FTY=16 -DVTI_FT_MINB=8
-build F_B_minb5_lut8 -DVTI_K1_LWT=1 -DVTI_K1_STAGE2=0 -DVTI_K1_LUT8=1
-build r1nf -DVTI_K1_STAGE2=0 -DVTI_K1_DIVFMA=0 -DVTI_K1_PADROWS=0
+build A_early3
+build B_early1 -DVTI_K1_EARLY=1
+build C_early2 -DVTI_K1_EARLY=2
+build D_early0 -DVTI_K1_EARLY=0
+build E_early3_reg56 -DVTI_K1_MAXREG=56
+build F_early3_reg64 -DVTI_K1_MAXREG=64
+build G_early0_reg56 -DVTI_K1_EARLY=0 -DVTI_K1_MAXREG=56
 python vision_textile_inspection_b200/build.py --force > /dev/null   # leave the default objects in build/

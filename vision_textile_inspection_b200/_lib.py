@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("VTI_LIB", os.path.join(HERE, "libvti.so"))
 
 VTI_NM = 32
 F_IN_ROI, F_STITCH, F_FABRIC, F_HAS_MASK, F_SELECTED, F_FINAL, F_HAS_WIDTH, F_HAS_DIST = 1, 2, 4, 8, 16, 32, 64, 128
+F_LB_MASK, F_DROPPED = 256, 512
 ST_OK, ST_NO_FABRIC, ST_NO_STITCH, ST_OVERFLOW = 0, 2, 3, 0x100
 
 
@@ -25,7 +26,7 @@ class VtiParams(C.Structure):
         ("max_px_distance", C.c_int32), ("neighborhood", C.c_int32), ("max_candidates", C.c_int32),
         ("conf", C.c_float), ("iou", C.c_float),
         ("K", C.c_double * 9), ("dist", C.c_double * 5), ("R", C.c_double * 9), ("t", C.c_double * 3),
-        ("iou_threshold", C.c_double),
+        ("iou_threshold", C.c_double), ("mask_variant", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -43,7 +44,7 @@ DET_DTYPE = np.dtype([
     ("box_lb", "<f4", 4), ("box_frame", "<f4", 4), ("box_int", "<i4", 4), ("conf", "<f4"), ("cls", "<i4"),
     ("anchor", "<i4"), ("flags", "<u4"), ("m00", "<i8"), ("m10", "<i8"), ("m01", "<i8"), ("col_min", "<i4"),
     ("col_max", "<i4"), ("cx", "<f8"), ("cy", "<f8"), ("left_px", "<f8"), ("right_px", "<f8"), ("width_mm", "<f8"),
-    ("edge_y", "<f8"), ("dist_mm", "<f8"), ("reserved", "<f8"),
+    ("edge_y", "<f8"), ("dist_mm", "<f8"), ("area_mm2", "<f8"),
 ])
 RESULT_DTYPE = np.dtype([
     ("status", "<i4"), ("n_det", "<i4"), ("n_cand", "<i4"), ("n_stitch", "<i4"), ("n_fabric", "<i4"),

@@ -115,7 +115,7 @@ class B200Predictor:
     """
 
     def __init__(self, backbone, K, dist, R=None, t=None, device=None, undistort=0, nc=2, roi=(0, 0, 0, 0, 0),
-                 variant=0, channel_flip=1):
+                 variant=0, channel_flip=1, mask_variant=0):
         if not torch.cuda.is_available():
             raise _lib.VtiError("B200Predictor needs a CUDA device: the hot path has no CPU fallback")
         self.backbone = backbone
@@ -124,6 +124,7 @@ class B200Predictor:
         self.t = np.array([0.0, 0.0, 1.0]) if t is None else np.asarray(t, np.float64)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.undistort, self.nc, self.roi, self.variant, self.channel_flip = undistort, nc, roi, variant, channel_flip
+        self.mask_variant = mask_variant      # 0: Ultralytics <= 8.0.x masks (sigmoid, > 0.5); 1: newer (logits, > 0, drop)
         self.extra = {}
         self._engines = {}
 
@@ -133,7 +134,8 @@ class B200Predictor:
         if eng is None:
             ec = EngineConfig(frame_h=h, frame_w=w, K=self.K, dist=self.dist, R=self.R, t=self.t, imgsz=imgsz,
                               nc=self.nc, conf=conf, iou=iou, max_det=max_det, max_batch=batch, variant=self.variant,
-                              undistort=self.undistort, channel_flip=self.channel_flip, roi=self.roi, **self.extra)
+                              undistort=self.undistort, channel_flip=self.channel_flip, roi=self.roi,
+                              mask_variant=self.mask_variant, **self.extra)
             eng = self._engines[key] = InspectionEngine(ec, self.device)
         return eng
 
@@ -155,9 +157,13 @@ class B200Predictor:
         for b in range(frames.shape[0]):
             n = int(counts[b])
             d = dets[b, :n]
+            md = eng.unpack_masks(masks, b, n).cpu() if n else None
+            if n and self.mask_variant == 1:              # newer Ultralytics removes detections with an empty mask
+                keep = (d["flags"] & _lib.F_DROPPED) == 0
+                d, md = d[keep], md[torch.from_numpy(keep)]
             boxes = _Boxes(torch.from_numpy(d["cls"].astype(np.float32)), torch.from_numpy(d["box_frame"].copy()),
                            torch.from_numpy(d["conf"].copy()))
-            m = _Masks(eng.unpack_masks(masks, b, n).cpu()) if n else None
+            m = _Masks(md) if len(d) else None
             out.append(Results(boxes, m, d, results[b]))
         return out
 
@@ -169,11 +175,13 @@ class StitchMeasurementApp:
     module docstring; default = backbone_from_ultralytics(model_path)), `roi`, `conf`, `iou`, `max_det`, `imgsz`,
     `undistort`, `annotate`, `device`.  `camera_index=None` skips opening a camera (`.cap` is then None).
     """
+    VARIANT = 0          # measure-stage semantics: 0 = measurement.py, 1 = Utils/check_stitch_distance.py (subclass below)
 
     def __init__(self, calib_path, extr_path, model_path, camera_index=0, calib_w=640, calib_h=640, frame_buffer=8,
                  min_stitches=MIN_STITCHES, stitch_id=STITCH_CLASS_ID, fabric_id=FABRIC_CLASS_ID, *, backbone=None,
                  roi=ROI_DEFAULT, conf=CONF_THRESH, iou=IOU_THRESH, max_det=MAX_DETECTIONS, imgsz=960, undistort=0,
-                 max_px_distance=MAX_PX_DISTANCE, neighborhood=ENVELOPE_NEIGHBORHOOD, annotate=True, device=None):
+                 max_px_distance=MAX_PX_DISTANCE, neighborhood=ENVELOPE_NEIGHBORHOOD, annotate=True, device=None,
+                 mask_variant=0):
         if not os.path.exists(calib_path):
             raise FileNotFoundError(f"Calibration file missing: {calib_path}")
         calib = load_json(calib_path)
@@ -196,7 +204,8 @@ class StitchMeasurementApp:
         if backbone is None:
             backbone = backbone_from_ultralytics(model_path)
         self.model = B200Predictor(backbone, self.K, self.dist, self.R, self.t, device=device, undistort=undistort,
-                                   roi=tuple(int(v) for v in roi), channel_flip=0)   # frames arrive BGR: no flip
+                                   roi=tuple(int(v) for v in roi), channel_flip=0,   # frames arrive BGR: no flip
+                                   variant=self.VARIANT, mask_variant=mask_variant)
         self.model.extra = dict(min_stitches=min_stitches, stitch_id=stitch_id, fabric_id=fabric_id,
                                 max_px_distance=max_px_distance, neighborhood=neighborhood)
         self.conf, self.iou, self.max_det, self.imgsz = conf, iou, max_det, imgsz
@@ -297,6 +306,20 @@ class StitchMeasurementApp:
             text = f"Insufficient stitches (need {self.min_stitches})"
         cv2.putText(img, text, (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 0.7, (0, 0, 255), 2)
 
+    def _info_text(self, r) -> str:
+        """Utils/check_stitch_distance.py:513-540 (smoothing + the text line it returns and draws)."""
+        ad = None if np.isnan(r["avg_dist"]) else float(r["avg_dist"])
+        aw = None if np.isnan(r["avg_width"]) else float(r["avg_width"])
+        sd, sw = self._smooth(ad, aw)
+        n_found = int(r["n_width"])
+        if sd is not None and sw is not None:
+            return f"Edge Dist: {sd:.2f}mm | Avg Width: {sw:.2f}mm (n={n_found})"
+        if sd is not None:
+            return f"Edge Distance: {sd:.2f}mm (n={n_found})"
+        if sw is not None:
+            return f"Avg Width: {sw:.2f}mm (n={n_found})"
+        return f"Insufficient stitches (found {n_found}, need {self.min_stitches})"
+
     def run(self):  # pragma: no cover - camera loop of measurement.py:513-560, needs hardware
         last = 0.0
         while self.running and self.cap is not None:
@@ -309,3 +332,49 @@ class StitchMeasurementApp:
                 last = time.time()
         if self.cap is not None:
             self.cap.release()
+
+
+class CheckStitchDistanceApp(StitchMeasurementApp):
+    """Outer drop-in for BASELINE config 3: the class /root/reference/Utils/check_stitch_distance.py:176 also calls
+    StitchMeasurementApp, whose process_frame (:281-553) returns `(annotated, info_text)` -- a string, not a dict.
+
+    Same constructor signature (:177-187); semantics of that file: no ROI, predict() without imgsz (Ultralytics'
+    default 640, :286), upper fabric envelope, mask-less fabric detections as filled boxes, `0 < d < 150` proximity
+    rule, widths of the final stitches only, k-means labels updated on break -- all inside libvti (variant = 1).
+    Error returns: "Model error" (:291), "Fabric not detected" (:347), "No stitches detected" (:406)."""
+    VARIANT = 1
+
+    def __init__(self, calib_path, extr_path, model_path, camera_index=0, calib_w=640, calib_h=640, frame_buffer=8,
+                 min_stitches=MIN_STITCHES, stitch_id=STITCH_CLASS_ID, fabric_id=FABRIC_CLASS_ID, **kw):
+        kw.setdefault("roi", (0, 0, 0, 0, 0))
+        kw.setdefault("imgsz", 640)
+        kw.setdefault("max_px_distance", 150)              # check_stitch_distance.py:38
+        super().__init__(calib_path, extr_path, model_path, camera_index, calib_w, calib_h, frame_buffer, min_stitches,
+                         stitch_id, fabric_id, **kw)
+
+    def process_frames(self, frames: np.ndarray):
+        """(B,h,w,3) uint8 -> list of info_text strings, smoothing in frame order."""
+        eng, dets, counts, results, _ = self.model.run(frames, self.conf, self.iou, self.max_det, self.imgsz,
+                                                       export_masks=False)
+        self.last_records = [dets[b, :int(counts[b])] for b in range(frames.shape[0])]
+        out = []
+        for b in range(frames.shape[0]):
+            status = int(results[b]["status"]) & 0xFF
+            out.append(_ERRORS[status] if status in _ERRORS else self._info_text(results[b]))
+        return out
+
+    def process_frame(self, frame):
+        """frame: h x w x 3 uint8 BGR (not mutated).  Returns (annotated, info_text); never raises."""
+        try:
+            text = self.process_frames(np.ascontiguousarray(frame)[None])[0]
+        except Exception as e:
+            print("Model inference error:", e)
+            return frame.copy(), "Model error"
+        annotated = frame.copy()
+        if self.annotate and text not in _ERRORS.values():
+            try:
+                import cv2
+                cv2.putText(annotated, text, (10, 30), cv2.FONT_HERSHEY_SIMPLEX, 0.7, (0, 0, 255), 2)
+            except Exception:  # pragma: no cover
+                pass
+        return annotated, text

@@ -211,9 +211,10 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     }
     // nc: K2 packs the class into the top byte of a candidate key; max_batch: K3 packs the frame index into 15 bits
     if (p->nc < 1 || p->nc > 255 || p->max_det < 1 || p->max_det > 1024 || p->max_batch < 1 || p->max_batch > 32767 ||
-        p->neighborhood < 0 || p->neighborhood > 7 || (p->variant != 0 && p->variant != 1)) {
+        p->neighborhood < 0 || p->neighborhood > 7 || (p->variant != 0 && p->variant != 1) ||
+        (p->mask_variant != 0 && p->mask_variant != 1)) {
         vti_set_error("vti_create: parameter out of range (nc 1..255, max_det 1..1024, max_batch 1..32767, "
-                      "neighborhood 0..7, variant 0/1)");
+                      "neighborhood 0..7, variant 0/1, mask_variant 0/1)");
         return VTI_EINVAL;
     }
     int ndev = 0;

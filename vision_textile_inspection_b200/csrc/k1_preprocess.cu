@@ -304,21 +304,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 #ifndef VTI_K1_HSHARE
 #define VTI_K1_HSHARE 1
 #endif
-// round-2 instruction cuts (each can be switched off for A/B runs: tools/k1_sweep.sh)
-#ifndef VTI_K1_LUT8      // 8-byte remap entries (weights pre-decoded) + one raw pitch per handle (a uniform register)
-#define VTI_K1_LUT8 0
-#endif
-#ifndef VTI_K1_FIXPITCH  // one raw-box row pitch per handle, an immediate in the remap loads when it is K1_RAWP
-#define VTI_K1_FIXPITCH 1
-#endif
-#ifndef VTI_K1_MULHI     // V pass of the resize: (b * P) >> 16 as one mad.hi on b << 16
-#define VTI_K1_MULHI 0
-#endif
+// round-2 changes (each can be switched off for A/B runs: tools/k1_sweep.sh; what was tried and rejected: DESIGN.md 5)
 #ifndef VTI_K1_LWT       // output row pitch as a template constant: plane stores take immediate offsets
 #define VTI_K1_LWT 1
-#endif
-#ifndef VTI_K1_STAGE2    // staging: (row, group) per lane by shifts, two rows per warp pass, interior boxes unchecked
-#define VTI_K1_STAGE2 0
 #endif
 #ifndef VTI_K1_DIVFMA    // x / 255 as FMUL + FFMA on split constants (exact for 0..255) instead of a shared-memory table
 #define VTI_K1_DIVFMA 1
@@ -330,8 +318,12 @@ constexpr int FTX = VTI_FTX, FTY = VTI_FTY;  // fast-path output tile
 constexpr int FT_THREADS = VTI_FT_THREADS;
 constexpr int FT_CHUNK = 2 * FT_THREADS;     // the remap loop handles 2 entries per thread and iteration (prefetched)
 constexpr int FT_MAXROWS = 2 * FTY + 2, FT_MAXCOLS = 2 * FTX + 2;
-constexpr int K1_RAWP = 112;    // raw-box row pitch (words) baked into the remap kernel when no tile needs more
+#ifndef VTI_K1_RAWP
+#define VTI_K1_RAWP 112
+#endif
+constexpr int K1_RAWP = VTI_K1_RAWP;    // raw-box row pitch (words) baked into the remap kernel when no tile needs more
 
+#if !VTI_K1_DIVFMA
 // float32(i) / 255.0f (a true division, IEEE round-to-nearest), as bit patterns: i/255 for the 256 uint8 values.
 // Generated with numpy float32; tests/test_gpu_parity.py::test_k1_bit_exact compares every value against cv2 + torch.
 __device__ const unsigned g_div255_bits[256] = {
@@ -368,12 +360,13 @@ __device__ const unsigned g_div255_bits[256] = {
     0x3f70f0f1u, 0x3f71f1f2u, 0x3f72f2f3u, 0x3f73f3f4u, 0x3f74f4f5u, 0x3f75f5f6u, 0x3f76f6f7u, 0x3f77f7f8u,
     0x3f78f8f9u, 0x3f79f9fau, 0x3f7afafbu, 0x3f7bfbfcu, 0x3f7cfcfdu, 0x3f7dfdfeu, 0x3f7efeffu, 0x3f800000u,
 };
+#endif
 
 struct K1FastArgs {
     const uint8_t* frames;
     float* out;
     const int4* tile_hdr;       // [tiles][2]: (bx0, by0, bw, bh), (r_lo, c_lo, nrows, ncols)
-    const unsigned* lut;        // [tiles][lut_stride] entries of 4 bytes (8 with VTI_K1_LUT8)   (REMAP only)
+    const unsigned* lut;        // [tiles][lut_stride] 4-byte entries   (REMAP only)
     const int32_t* tap_x_idx;   // [new_w]
     const int16_t* tap_x_a;     // [new_w][2]
     const int32_t* tap_y_i;     // [new_h][2]
@@ -383,7 +376,7 @@ struct K1FastArgs {
     int pitch_u, rows_u;
     int und_words;              // words reserved for the footprint buffer (multiple of FT_CHUNK, > rows_u * pitch_u)
     int lut_stride;             // entries per tile (multiple of FT_CHUNK)
-    int raw_pitch;              // VTI_K1_LUT8: words per row of the raw box in shared memory (same for every tile)
+    int raw_pitch;              // words per row of the raw box in shared memory (the same for every tile)
 };
 
 // Stage rows [y0, y0+nr) x 8-pixel groups [x0, x0 + 8*ng) of the frame as packed words (B | G<<8 | R<<16, byte 3 = 0);
@@ -438,77 +431,6 @@ __device__ __forceinline__ void stage_box(const uint8_t* __restrict__ frame, int
     }
 }
 
-// Round-2 staging (VTI_K1_STAGE2).  K1 is bound by L1 data-pipe wavefronts, so the staging is organised around them:
-// a lane owns ONE 16-byte shared chunk = 4 pixels = 12 source bytes (three 32-bit loads; x0 % 4 == 0 and w % 4 == 0
-// keep them aligned and inside the row), a warp owns one box row per pass, so its single STS.128 writes consecutive
-// chunks: 4 wavefronts per 512 bytes, the minimum (the 8-pixel form writes two chunks per lane: 2-way bank conflicts,
-// 7.7 wavefronts per store measured).  The (row, chunk) of a lane costs no division.  The P passes of a box (8 rows
-// each; P = 4 or 3, picked per CTA) are straight-line code with 3 P loads in flight per lane before the first unpack;
-// only the shared store of a row past the box is predicated off.  A chunk outside the image (cv2.remap's
-// BORDER_CONSTANT zero margin) loads from a block of zeros instead: no zeroing instructions.
-__device__ const unsigned g_zero12[4] = {0u, 0u, 0u, 0u};
-
-template <int P>
-__device__ __forceinline__ void stage_rows(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int nc, int nr,
-                                           int rb0, unsigned* dst, int pitch, int tid, unsigned sel_lo, unsigned sel_hi) {
-    const int lane = tid & 31;
-    constexpr int NW = FT_THREADS / 32;
-    const int rb = rb0 + (tid >> 5);
-    for (int c = lane; c < nc; c += 32) {
-        const int x = x0 + 4 * c;
-        const bool xin = (unsigned)x < (unsigned)w;
-        unsigned q[P][3];
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            const int r = rb + NW * k, y = y0 + r;
-            const bool ok = (r < nr) && xin && ((unsigned)y < (unsigned)h);
-            const unsigned* __restrict__ src = ok ? reinterpret_cast<const unsigned*>(frame + (unsigned)(y * w + x) * 3u)
-                                                  : g_zero12;                             // frames are < 2^31 bytes
-            q[k][0] = __ldg(src); q[k][1] = __ldg(src + 1); q[k][2] = __ldg(src + 2);
-        }
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            const int r = rb + NW * k;
-            uint4 v;
-            v.x = __byte_perm(q[k][0], 0u, sel_lo);
-            v.y = __byte_perm(__funnelshift_r(q[k][0], q[k][1], 24), 0u, sel_lo);
-            v.z = __byte_perm(__funnelshift_r(q[k][1], q[k][2], 16), 0u, sel_lo);
-            v.w = __byte_perm(q[k][2], 0u, sel_hi);
-            if (r < nr) *reinterpret_cast<uint4*>(dst + r * pitch + 4 * c) = v;
-        }
-    }
-}
-// ng = 8-pixel groups per row (the plan sizes boxes in groups), nr rows
-__device__ __forceinline__ void stage_box2(const uint8_t* __restrict__ frame, int h, int w, int x0, int y0, int ng, int nr,
-                                           unsigned* dst, int pitch, int tid, int flip) {
-    const unsigned sel_lo = flip ? 0x4012u : 0x4210u, sel_hi = flip ? 0x4123u : 0x4321u;
-    constexpr int RPP = FT_THREADS / 32;                   // rows per pass
-    for (int rb0 = 0; rb0 < nr;) {                          // CTA-uniform control flow
-        if (nr - rb0 > 3 * RPP) { stage_rows<4>(frame, h, w, x0, y0, 2 * ng, nr, rb0, dst, pitch, tid, sel_lo, sel_hi); rb0 += 4 * RPP; }
-        else { stage_rows<3>(frame, h, w, x0, y0, 2 * ng, nr, rb0, dst, pitch, tid, sel_lo, sel_hi); rb0 += 3 * RPP; }
-    }
-}
-
-__device__ __forceinline__ unsigned remap_fast(const unsigned char* raw, unsigned e, unsigned bw4) {
-    const unsigned off = e >> 16;
-    const unsigned fx = e & 0xFFu, fy = __byte_perm(e, 0, 0x4441);
-    const unsigned t00 = *reinterpret_cast<const unsigned*>(raw + off);
-    const unsigned t01 = *reinterpret_cast<const unsigned*>(raw + off + 4);
-    const unsigned t10 = *reinterpret_cast<const unsigned*>(raw + off + bw4);
-    const unsigned t11 = *reinterpret_cast<const unsigned*>(raw + off + bw4 + 4);
-    const unsigned wy0 = fy * 0xFFFFFFFFu + 32u;               // 32 - fy, as a multiply-add (FMA pipe)
-    const unsigned wxb = fx * 255u + 32u;                      // (32 - fx) | fx << 8
-    // rows blended for both columns at once: (V_x | V_x+1 << 16), each <= 8160
-    const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
-    const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
-    const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
-    // (acc + 512) >> 10 is an 8-bit value; << 6 parks it in byte 2 where PRMT can pick it up
-    const unsigned b = __dp2a_lo(vB, wxb, 512u) * 64u;
-    const unsigned g = __dp2a_lo(vG, wxb, 512u) * 64u;
-    const unsigned r = __dp2a_lo(vR, wxb, 512u) * 64u;
-    return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);           // bytes 3 of b, g, r are 0
-}
-
 // 32-bit shared-window addresses and ld.shared: the address of a tap is ONE integer add away from the per-thread
 // base (generic pointers cost an extra instruction per load to re-add the window base).
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -535,25 +457,6 @@ __device__ __forceinline__ unsigned remap_fast4(unsigned raw, unsigned e, unsign
     const unsigned b = __dp2a_lo(vB, wxb, 512u) * 64u;
     const unsigned g = __dp2a_lo(vG, wxb, 512u) * 64u;
     const unsigned r = __dp2a_lo(vR, wxb, 512u) * 64u;
-    return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);
-}
-
-// 8-byte entry: x = byte offset of the 2x2 neighbourhood << 16 | fx << 8 | (32 - fx)   (dp2a reads bytes 0, 1 as they are)
-//               y = fy << 16 | (32 - fy)
-// RAWP_T > 0: the raw box has that many words per row for every tile, so the second row is an immediate offset.
-template <int RAWP_T>
-__device__ __forceinline__ unsigned remap_fast8(unsigned raw, uint2 e, unsigned bw4) {
-    const unsigned p0 = raw + (e.x >> 16);
-    unsigned t00 = lds32<0>(p0), t01 = lds32<4>(p0), t10, t11;
-    if (RAWP_T > 0) { t10 = lds32<4 * RAWP_T>(p0); t11 = lds32<4 * RAWP_T + 4>(p0); }
-    else { t10 = lds32<0>(p0 + bw4); t11 = lds32<4>(p0 + bw4); }
-    const unsigned wy0 = e.y & 0xFFFFu, fy = e.y >> 16;
-    const unsigned vB = __byte_perm(t00, t01, 0x3430) * wy0 + __byte_perm(t10, t11, 0x3430) * fy;
-    const unsigned vG = __byte_perm(t00, t01, 0x3531) * wy0 + __byte_perm(t10, t11, 0x3531) * fy;
-    const unsigned vR = __byte_perm(t00, t01, 0x3632) * wy0 + __byte_perm(t10, t11, 0x3632) * fy;
-    const unsigned b = __dp2a_lo(vB, e.x, 512u) * 64u;
-    const unsigned g = __dp2a_lo(vG, e.x, 512u) * 64u;
-    const unsigned r = __dp2a_lo(vR, e.x, 512u) * 64u;
     return __byte_perm(__byte_perm(b, g, 0x7762), r, 0x7610);
 }
 
@@ -589,19 +492,6 @@ __device__ __forceinline__ void resize_px(const unsigned char* p0, const unsigne
     v0 = div255_q(qb, divb);
     v1 = div255_q(qg, divb);
     v2 = div255_q(qr, divb);
-}
-
-// mul.hi kept apart from the following add (as mad.hi, SASS IMAD.HI takes a 64-bit addend whose low word has to be
-// zeroed first: one extra move per use), and a three-input add (IADD3) for the two products and the rounding constant.
-__device__ __forceinline__ unsigned mulhi_nf(unsigned a, unsigned b) {
-    unsigned d;
-    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned add3(unsigned a, unsigned b, unsigned c) {
-    unsigned d;
-    asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
 }
 
 // float32(v) / 255.0f for q = 4 v + (0..3), v in 0..255, WITHOUT the table: x = float(4 v) is exact, 1/1020 is split
@@ -658,17 +548,10 @@ __device__ __forceinline__ void resize_strip(const int4* rowtap, unsigned col, u
         const unsigned nb = __dp2a_lo(a01, bg, 0u) >> 4, ng = __dp2a_hi(a01, bg, 0u) >> 4, nr = __dp2a_lo(a01, rr, 0u) >> 4;
         const unsigned b0 = (unsigned)rt.z, b1 = (unsigned)rt.w;
         unsigned qb, qg, qr;
-#if VTI_K1_MULHI
-        // ((b0 P0) >> 16) + ((b1 P1) >> 16) + 2 with b pre-shifted by 16: two mad.hi per channel
-        qb = add3(mulhi_nf(b0, pb), mulhi_nf(b1, nb), 2u);
-        qg = add3(mulhi_nf(b0, pg), mulhi_nf(b1, ng), 2u);
-        qr = add3(mulhi_nf(b0, pr), mulhi_nf(b1, nr), 2u);
-#else
         // PRMT takes both >> 16 at once, dp2a adds them.  The plan guarantees b0 + b1 <= 2049: no saturation needed.
         qb = __dp2a_lo(__byte_perm(b0 * pb, b1 * nb, 0x7632), 0x0101u, 2u);
         qg = __dp2a_lo(__byte_perm(b0 * pg, b1 * ng, 0x7632), 0x0101u, 2u);
         qr = __dp2a_lo(__byte_perm(b0 * pr, b1 * nr, 0x7632), 0x0101u, 2u);
-#endif
         store_px<LW_T>(o0, i, oi, div255_q(qb, divb));
         store_px<LW_T>(o1, i, oi, div255_q(qg, divb));
         store_px<LW_T>(o2, i, oi, div255_q(qr, divb));
@@ -679,7 +562,9 @@ __device__ __forceinline__ void resize_strip(const int4* rowtap, unsigned col, u
 template <bool REMAP, bool AREA, int LW_T, int RAWP_T>
 __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const K1FastArgs a) {
     extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [und_words], then the raw box (REMAP)
+#if !VTI_K1_DIVFMA
     __shared__ float s_div[256];
+#endif
     __shared__ int4 s_rowtap[FTY];                          // (byte offset row0, byte offset row1, b0, b1)
 
     const int tid = threadIdx.x;
@@ -693,7 +578,9 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
 
     const int4 h0 = __ldg(a.tile_hdr + 2 * tile), h1 = __ldg(a.tile_hdr + 2 * tile + 1);
     const int r_lo = h1.x, c_lo = h1.y, nrows = h1.z;
+#if !VTI_K1_DIVFMA
     for (int i = tid; i < 256; i += FT_THREADS) s_div[i] = __uint_as_float(g_div255_bits[i]);
+#endif
     if (tid < FTY) {
         const int ry = Y0 + tid - a.top;
         int4 t = make_int4(-2, -2, 0, 0);                   // padding row (never equal to a real row offset)
@@ -702,49 +589,25 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
             t.y = (a.tap_y_i[2 * ry + 1] - r_lo) * a.pitch_u * 4;
             t.z = a.tap_y_b[2 * ry];
             t.w = a.tap_y_b[2 * ry + 1];
-            if (VTI_K1_MULHI && !AREA) { t.z <<= 16; t.w <<= 16; }      // b <= 2048: mad.hi operands
         }
         s_rowtap[tid] = t;
     }
 
+
     // ------------------------------------------------------------------------------------------- stage (+ remap)
     if (nrows > 0) {
         if (!REMAP) {
-#if VTI_K1_STAGE2
-            stage_box2(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 3, nrows, s_und, a.pitch_u, tid, a.flip);
-#else
             stage_box(frame, a.h, a.w, c_lo, r_lo, a.pitch_u >> 3, nrows, s_und, tid, a.flip);
-#endif
         } else {
             unsigned* s_raw = s_dyn + a.und_words;
-#if VTI_K1_STAGE2
-            const int rp = VTI_K1_FIXPITCH ? (RAWP_T > 0 ? RAWP_T : a.raw_pitch) : h0.z;
-            stage_box2(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, rp, tid, a.flip);
-#else
-            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, tid, a.flip, VTI_K1_FIXPITCH ? a.raw_pitch : 0);
-#endif
+            stage_box(frame, a.h, a.w, h0.x, h0.y, h0.z >> 3, h0.w, s_raw, tid, a.flip, a.raw_pitch);
             __syncthreads();
-            const unsigned char* raw = reinterpret_cast<const unsigned char*>(s_raw);
             unsigned* dst = s_und + tid;
             const int total = nrows * a.pitch_u;
             const int n_it = total / FT_CHUNK;                 // whole chunks; table and buffer are padded
             const int rem = total - n_it * FT_CHUNK;
             const unsigned raw8 = smem_addr(s_raw);
-#if VTI_K1_LUT8
             const unsigned bw4 = (unsigned)a.raw_pitch * 4u;
-            const uint2* __restrict__ lut = reinterpret_cast<const uint2*>(a.lut) + (size_t)tile * a.lut_stride + tid;
-            uint2 e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
-            for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
-                lut += FT_CHUNK;                               // next entries in flight while these are computed
-                const uint2 n0 = __ldg(lut), n1 = __ldg(lut + FT_THREADS);       // (the table has one spare chunk)
-                dst[0] = remap_fast8<RAWP_T>(raw8, e0, bw4);
-                dst[FT_THREADS] = remap_fast8<RAWP_T>(raw8, e1, bw4);
-                e0 = n0; e1 = n1;
-            }
-            if (tid < rem) dst[0] = remap_fast8<RAWP_T>(raw8, e0, bw4);
-            if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast8<RAWP_T>(raw8, e1, bw4);
-#else
-            const unsigned bw4 = (unsigned)(VTI_K1_FIXPITCH ? a.raw_pitch : h0.z) * 4u;
             const unsigned* __restrict__ lut = a.lut + (size_t)tile * a.lut_stride + tid;
             unsigned e0 = __ldg(lut), e1 = __ldg(lut + FT_THREADS);
             for (int it = 0; it < n_it; ++it, dst += FT_CHUNK) {
@@ -757,13 +620,12 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
             // tail of the footprint: only the warps that still have cells (a 44 x 87 footprint leaves 244 of 512)
             if (tid < rem) dst[0] = remap_fast4<RAWP_T>(raw8, e0, bw4);
             if (tid + FT_THREADS < rem) dst[FT_THREADS] = remap_fast4<RAWP_T>(raw8, e1, bw4);
-#endif
         }
     }
     __syncthreads();
 
     // ----------------------------------------------------------------------------------------------- resize
-    const float pad = s_div[114];
+    const float pad = __uint_as_float(0x3ee4e4e5u);            // float32(114) / 255.0f, the LetterBox border
     const int X = X0 + (tid & (FTX - 1));
     if (X >= LW) return;
     constexpr int RPT = FTY / (FT_THREADS / FTX);          // rows per thread
@@ -785,9 +647,13 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
         return;
     }
     const int sx = a.tap_x_idx[rx];
-    const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
     const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
+    const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
+#if VTI_K1_DIVFMA
+    const unsigned char* divb = nullptr;
+#else
     const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
+#endif
     const bool full = (ry0 >= 0) && (ry0 + RPT <= a.new_h) && (n_out == RPT);      // warp-uniform
     if (!AREA && VTI_K1_HSHARE && full) {
         resize_strip<LW_T, false>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, RPT, pad);
@@ -798,8 +664,7 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
             const int4 rt = s_rowtap[j0 + i];
             float v0 = pad, v1 = pad, v2 = pad;
             if (rt.x >= 0) {
-                const unsigned sh = (VTI_K1_MULHI && !AREA) ? 16u : 0u;
-                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z >> sh, (unsigned)rt.w >> sh, divb, v0, v1, v2);
+                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
             }
             store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
         }
@@ -887,19 +752,18 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
         bh_max = std::max(bh_max, bh);
         hdr[2 * t] = make_int4(bx0, by0, bw, bh);
     }
-    const int esz = VTI_K1_LUT8 ? 2 : 1;                            // words per entry
-    if (VTI_K1_FIXPITCH) {
+    {                                                               // every tile's raw box at ONE pitch
         if (raw_pitch <= K1_RAWP) raw_pitch = K1_RAWP;              // the pitch the kernel has as an immediate
         if ((size_t)raw_pitch * bh_max > 16384) return false;
         raw_words = (size_t)raw_pitch * bh_max;                     // every tile's box at the one pitch
     }
-    lut.assign((ntiles * lut_stride + FT_CHUNK) * esz, 0u);         // + one spare chunk: the loop prefetches
+    lut.assign(ntiles * lut_stride + FT_CHUNK, 0u);         // + one spare chunk: the loop prefetches
     for (size_t t = 0; t < ntiles; ++t) {
         const int4 f = hdr[2 * t + 1], bx = hdr[2 * t];
         const int r_lo = f.x, c_lo = f.y, nrows = f.z;
         if (nrows == 0) continue;
-        const int bx0 = bx.x, by0 = bx.y, bw = VTI_K1_FIXPITCH ? raw_pitch : bx.z;
-        unsigned* L = lut.data() + t * lut_stride * esz;
+        const int bx0 = bx.x, by0 = bx.y, bw = raw_pitch;
+        unsigned* L = lut.data() + t * lut_stride;
         for (int r = 0; r < nrows; ++r)
             for (int c = 0; c < pitch_u; ++c) {
                 const int sy = r_lo + r, sx = c_lo + c;
@@ -912,12 +776,7 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
                     fx = (unsigned)(ix & 31); fy = (unsigned)(iy & 31);
                 }
                 const size_t e = (size_t)r * pitch_u + c;
-                if (VTI_K1_LUT8) {
-                    L[2 * e] = (off << 16) | (fx << 8) | (32u - fx);
-                    L[2 * e + 1] = (fy << 16) | (32u - fy);
-                } else {
-                    L[e] = (off << 16) | (fy << 8) | fx;
-                }
+                L[e] = (off << 16) | (fy << 8) | fx;
             }
     }
     return true;

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_nms_kernel(const K3Args a) {
         d.col_min = INT_MAX; d.col_max = -1;
         const double qnan = __longlong_as_double(0x7ff8000000000000LL);
         d.cx = qnan; d.cy = qnan; d.left_px = qnan; d.right_px = qnan;
-        d.width_mm = qnan; d.edge_y = qnan; d.dist_mm = qnan; d.reserved = 0.0;
+        d.width_mm = qnan; d.edge_y = qnan; d.dist_mm = qnan; d.area_mm2 = qnan;
         dets[tid] = d;
         const bool wanted = a.all_dets || ((f & VTI_F_IN_ROI) && (f & (VTI_F_STITCH | VTI_F_FABRIC)));
         const VtiWindow w = vti_det_window(d.box_lb, a.ph, a.pw);

@@ -24,6 +24,9 @@
 //       few lanes hold one).
 //   (3) warp reduction (three REDUX on 32-bit per-unit sums), one set of 64-bit global atomics per unit.
 // Optional bit-packed mask export: cells OR their bits into the (pre-zeroed) global mask words.
+// Mask variant B (vti_params.mask_variant = 1, newer Ultralytics: SURVEY 8a U6) is the same kernel in another threshold
+// domain (template parameter VB): the corner values are the raw logits (no sigmoid), cropped-out corners are 0, the
+// threshold is > 0.0; K5 then drops the detections whose letterbox mask stayed empty (flag VTI_F_LB_MASK never set).
 // Bound: the prototype read (128 B per prototype pixel touched); algorithmic bytes 128*ph*pw per frame.
 #include <climits>
 #include <cstdlib>
@@ -42,6 +45,7 @@ constexpr int NWARP = K4_THREADS / 32;
 constexpr int UR = VTI_K4_UR, UC = VTI_K4_UC;
 constexpr int SCW = UC + 1;                 // corner columns per unit
 constexpr float MARGIN = 1e-5f;             // >> fp32 rounding of the lerp; cells within the margin are evaluated per pixel
+constexpr float MARGIN_B = 1e-3f;           // variant B: logits (|values| up to ~30) instead of probabilities
 
 struct K4Args {
     const float* proto;         // [B][32][ph][pw]
@@ -66,10 +70,12 @@ __global__ void k4_zero_masks_kernel(uint32_t* masks, const int32_t* counts, int
 
 // Phases 2 and 3 of a unit: classify the interpolation cells from the corner values `sc` (pitch SCW), accumulate the
 // nearest-resize statistics, flush the unit's fabric envelope and reduce across the warp.
-template <bool EXPORT>
+template <bool EXPORT, bool VB>
 __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_det* __restrict__ det, bool fabric, int R0,
                                            int C0, int nr, int ncw, const float* sc, int* envw, int lane) {
     const int ex0 = 4 * C0 - 2;                            // first output column of the unit
+    constexpr float THR = VB ? 0.0f : 0.5f, MRG = VB ? MARGIN_B : MARGIN;
+    bool any = false;                                      // a letterbox pixel of this detection is set
     // (2) cells
     const int ncc = ncw - 1;
     const float inv_ncc = 1.0f / (float)ncc;
@@ -94,8 +100,9 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
         }
         const float vmin = fminf(fminf(c00, c01), fminf(c10, c11));
         const float vmax = fmaxf(fmaxf(c00, c01), fmaxf(c10, c11));
-        const bool full = valid && vmin > 0.5f + MARGIN;
+        const bool full = valid && vmin > THR + MRG;
         if (full) {
+            any = true;
             // fully set: closed form from the prefix sums of the nearest-resize multiplicity tables
             const int f_cy = a.ly.pc[yb + 1] - a.ly.pc[ya], f_sy = a.ly.ps[yb + 1] - a.ly.ps[ya];
             const int f_cx = a.lx.pc[xb + 1] - a.lx.pc[xa], f_sx = a.lx.ps[xb + 1] - a.lx.ps[xa];
@@ -123,7 +130,7 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
         // Boundary cells evaluate their 16 pixels (torch upsample_bilinear2d, align_corners=False, scale 1/4).  Few lanes
         // of a warp hold one -- the mask edge crosses a unit as a line -- so the warp takes them two at a time, one
         // pixel per lane, instead of every holder looping over its 16 pixels with the other lanes idle.
-        unsigned bm = __ballot_sync(0xffffffffu, valid && !full && vmax >= 0.5f - MARGIN);
+        unsigned bm = __ballot_sync(0xffffffffu, valid && !full && vmax >= THR - MRG);
         while (bm) {
             const int s0 = __ffs(bm) - 1;
             bm &= bm - 1;
@@ -141,7 +148,8 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
                 const float top = (1.0f - lx1) * q00 + lx1 * q01;
                 const float bot = (1.0f - lx1) * q10 + lx1 * q11;
                 const float v = (1.0f - ly1) * top + ly1 * bot;
-                if (v > 0.5f) {
+                if (v > THR) {
+                    any = true;
                     const int cY = a.ly.cnt[Y], sY = a.ly.sum[Y], cX = a.lx.cnt[X];
                     m00 += cY * cX; m10 += cY * a.lx.sum[X]; m01 += sY * cX;
                     if (cY > 0 && cX > 0) {
@@ -168,6 +176,7 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
         }
     }
     // (3) warp reduction, one set of global atomics per unit
+    if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&det->flags, VTI_F_LB_MASK);
     m00 = __reduce_add_sync(0xffffffffu, m00);
     if (m00 > 0u) {
         m10 = __reduce_add_sync(0xffffffffu, m10);
@@ -184,7 +193,7 @@ __device__ __forceinline__ void unit_cells(const K4Args& a, int b, int k, vti_de
     }
 }
 
-template <bool EXPORT>
+template <bool EXPORT, bool VB>
 __global__ void __launch_bounds__(K4_THREADS, 1024 / K4_THREADS) k4_units_kernel(const K4Args a) {
     __shared__ float s_c[NWARP][(UR + 1) * SCW];
     __shared__ __align__(16) float s_coef[NWARP][VTI_NM];   // registers go to the 32 in-flight prototype loads
@@ -236,12 +245,12 @@ __global__ void __launch_bounds__(K4_THREADS, 1024 / K4_THREADS) k4_units_kernel
                     acc = fmaf(cf.x, pv[q], acc); acc = fmaf(cf.y, pv[q + 1], acc);
                     acc = fmaf(cf.z, pv[q + 2], acc); acc = fmaf(cf.w, pv[q + 3], acc);
                 }
-                v = 1.0f / (1.0f + expf(-acc));
+                v = VB ? acc : 1.0f / (1.0f + expf(-acc));
             }
             sc[r * SCW + c] = v;
         }
         __syncwarp();
-        unit_cells<EXPORT>(a, b, k, det, fabric, R0, C0, nr, ncw, sc, s_envw[warp], lane);
+        unit_cells<EXPORT, VB>(a, b, k, det, fabric, R0, C0, nr, ncw, sc, s_envw[warp], lane);
     }
 }
 
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(T_WARPS * 32, 2) k4_tma_kernel(const __grid_co
             sc[r * SCW + c] = v;
         }
         __syncwarp();
-        unit_cells<EXPORT>(a, g.b, g.k, det, g.fabric, g.R0, g.C0, g.nr, g.ncw, sc, s_envw[warp], lane);
+        unit_cells<EXPORT, false>(a, g.b, g.k, det, g.fabric, g.R0, g.C0, g.nr, g.ncw, sc, s_envw[warp], lane);
         __syncwarp();                                                   // everyone is done with box[cur], s_c, s_coef
         if (!more) break;
         g = gn; u = un;
@@ -436,7 +445,8 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
     CUtensorMap tmap;
     // OPT-IN (VTI_K4_TMA=1): measured on B200 the TMA form is 2x SLOWER than the LDG form (137 vs 70 us per 64 frames):
     // a unit's box is 128 rows of 96 bytes, and the TMA unit's per-row request rate, not bandwidth or latency, bounds it.
-    bool tma = g_encode_tiled && getenv("VTI_K4_TMA") && (reinterpret_cast<uintptr_t>(proto) & 15) == 0 &&
+    const bool vb = h->p.mask_variant == 1;
+    bool tma = g_encode_tiled && getenv("VTI_K4_TMA") && !vb && (reinterpret_cast<uintptr_t>(proto) & 15) == 0 &&
                (a.pw % 4) == 0;
     if (tma) {
         const cuuint64_t gdim[3] = {(cuuint64_t)a.pw, (cuuint64_t)a.ph, (cuuint64_t)VTI_NM * B};
@@ -457,8 +467,10 @@ int vti_launch_k4(vti_handle* h, const float* proto, int B, vti_det* dets, const
         // (no remap, no resize: cfg4) K4 is on the critical path and keeps the four.  VTI_K4_GRID overrides.
         const bool k1_heavy = h->p.undistort || h->p.frame_w != h->g.new_w || h->p.frame_h != h->g.new_h;
         const int grid = (getenv("VTI_K4_GRID") ? atoi(getenv("VTI_K4_GRID")) : (k1_heavy ? 2 : 4)) * h->num_sms;
-        if (masks) k4_units_kernel<true><<<grid, K4_THREADS, 0, s>>>(a);
-        else k4_units_kernel<false><<<grid, K4_THREADS, 0, s>>>(a);
+        if (masks && vb) k4_units_kernel<true, true><<<grid, K4_THREADS, 0, s>>>(a);
+        else if (masks) k4_units_kernel<true, false><<<grid, K4_THREADS, 0, s>>>(a);
+        else if (vb) k4_units_kernel<false, true><<<grid, K4_THREADS, 0, s>>>(a);
+        else k4_units_kernel<false, false><<<grid, K4_THREADS, 0, s>>>(a);
     }
     h->launches++;
     VTI_CUDA(cudaGetLastError());

@@ -40,6 +40,7 @@ struct K5Args {
     Camera cam;
     int max_det, LW, w, h;
     int variant, min_stitches, max_px, nb;
+    int mask_variant;
 };
 
 __device__ __forceinline__ bool pixel_to_world(const Camera& c, double u, double v, double out[3]) {
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     __shared__ short s_sel[MAXN];         // selected -> stitch index
     __shared__ short s_fin[MAXN];
     __shared__ unsigned char s_lab[MAXN], s_new[MAXN], s_pass[MAXN];
-    __shared__ int s_ns, s_nsel, s_nfin, s_nfab;
+    __shared__ int s_ns, s_nsel, s_nfin, s_nfab, s_ndrop;
     __shared__ long long s_envsum;
     __shared__ int s_envcnt;
 
@@ -177,12 +178,34 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     const Camera& cam = a.cam;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    if (tid == 0) { s_envsum = 0; s_envcnt = 0; s_nfab = 0; s_ns = 0; }
+    if (tid == 0) { s_envsum = 0; s_envcnt = 0; s_nfab = 0; s_ns = 0; s_ndrop = 0; }
+    __syncthreads();
     // ---- finalize K4's statistics, frame-resolution envelope
     for (int k = tid; k < n; k += K5_THREADS) {
         unsigned f = dets[k].flags;
-        if (dets[k].m00 > 0) { f |= VTI_F_HAS_MASK; dets[k].flags = f; }
-        else { dets[k].col_min = -1; dets[k].col_max = -1; }
+        const long long m00 = dets[k].m00;
+        if (a.mask_variant == 1 && !(f & VTI_F_LB_MASK)) {
+            // newer Ultralytics (construct_result): `keep = masks.amax((-2, -1)) > 0` removes the detection
+            f |= VTI_F_DROPPED;
+            atomicAdd(&s_ndrop, 1);
+        }
+        if (m00 > 0) {
+            f |= VTI_F_HAS_MASK;
+            // Area of the bitmap on the fabric plane (north-star "area"; spec: oracle/measure_port.py defect_area_mm2):
+            // m00 pixels x the plane area of one pixel at the centroid, |dP/du x dP/dv| by central differences.
+            const double cx = (double)dets[k].m10 / (double)m00, cy = (double)dets[k].m01 / (double)m00;
+            double pu0[3], pu1[3], pv0[3], pv1[3];
+            if (pixel_to_world(cam, cx - 0.5, cy, pu0) && pixel_to_world(cam, cx + 0.5, cy, pu1) &&
+                pixel_to_world(cam, cx, cy - 0.5, pv0) && pixel_to_world(cam, cx, cy + 0.5, pv1)) {
+                const double ux = pu1[0] - pu0[0], uy = pu1[1] - pu0[1], uz = pu1[2] - pu0[2];
+                const double vx = pv1[0] - pv0[0], vy = pv1[1] - pv0[1], vz = pv1[2] - pv0[2];
+                const double c0 = uy * vz - uz * vy, c1 = uz * vx - ux * vz, c2 = ux * vy - uy * vx;
+                dets[k].area_mm2 = (double)m00 * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 1e6;
+            }
+        } else {
+            dets[k].col_min = -1; dets[k].col_max = -1;
+        }
+        dets[k].flags = f;
         s_flags[k] = f;
     }
     const int* __restrict__ env = a.env + (size_t)b * a.LW;
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         // mask-less fabric detection -> filled bbox rectangle (check_stitch_distance.py:331-334), upper envelope
         for (int k = 0; k < n; ++k) {
             const unsigned f = s_flags[k];
-            if (!(f & VTI_F_FABRIC) || (f & VTI_F_HAS_MASK)) continue;
+            if (!(f & VTI_F_FABRIC) || (f & VTI_F_HAS_MASK) || (f & VTI_F_DROPPED)) continue;
             const int x1 = max(min(dets[k].box_int[0], dets[k].box_int[2]), 0);
             const int x2 = min(max(dets[k].box_int[0], dets[k].box_int[2]), a.w - 1);
             const int y1 = max(min(dets[k].box_int[1], dets[k].box_int[3]), 0);
@@ -228,7 +251,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         for (int base = 0; base < n; base += 32) {
             const int k = base + lane;
             const unsigned f = k < n ? s_flags[k] : 0u;
-            const bool roi = f & VTI_F_IN_ROI;
+            const bool roi = (f & VTI_F_IN_ROI) && !(f & VTI_F_DROPPED);
             const bool st = roi && (f & VTI_F_STITCH);
             const bool fb = roi && !(f & VTI_F_STITCH) && (f & VTI_F_FABRIC) && ((f & VTI_F_HAS_MASK) || a.variant == 1);
             const unsigned ms = __ballot_sync(0xffffffffu, st), mf = __ballot_sync(0xffffffffu, fb);
@@ -242,7 +265,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     const int ns = s_ns;
     vti_frame_result r;
     r.status = VTI_ST_OK;
-    r.n_det = n;
+    r.n_det = n - s_ndrop;
     r.n_cand = a.flags[b] >> 8;
     r.n_stitch = ns;
     r.n_fabric = s_nfab;
@@ -468,6 +491,7 @@ int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vt
     c.d_c = -(c.n[0] * p.t[0] + c.n[1] * p.t[1] + c.n[2] * p.t[2]);     // measurement.py:47
     a.max_det = p.max_det; a.LW = h->g.LW; a.w = p.frame_w; a.h = p.frame_h;
     a.variant = p.variant; a.min_stitches = p.min_stitches; a.max_px = p.max_px_distance; a.nb = p.neighborhood;
+    a.mask_variant = p.mask_variant;
     k5_measure_kernel<<<B, K5_THREADS, 0, s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());

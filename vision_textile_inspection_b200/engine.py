@@ -62,6 +62,7 @@ class EngineConfig:
     max_px_distance: int = 250
     neighborhood: int = 3
     max_candidates: int = 0
+    mask_variant: int = 0         # 0 = "A" (sigmoid, > 0.5), 1 = "B" (newer Ultralytics: logits, > 0.0, empty masks dropped)
 
     @staticmethod
     def for_workload(cfg, calib: dict | None = None, max_batch: int | None = None) -> "EngineConfig":
@@ -90,6 +91,7 @@ class EngineConfig:
         p.roi_enabled, p.roi_x_min, p.roi_x_max, p.roi_y_min, p.roi_y_max = [int(v) for v in self.roi]
         p.min_stitches, p.max_px_distance, p.neighborhood = self.min_stitches, self.max_px_distance, self.neighborhood
         p.max_candidates = self.max_candidates
+        p.mask_variant = int(self.mask_variant)
         p.conf, p.iou = self.conf, self.iou
         p.iou_threshold = float(self.iou)          # the Python float torchvision.ops.nms receives (a C++ double)
         p.K[:] = np.asarray(self.K, np.float64).reshape(9).tolist()
