@@ -254,6 +254,172 @@ def run_reference(args, cfg, rank, world):
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
+def _allgather_floats(vals, world, dev):
+    """Every rank's list of floats -> (world, len) numpy array on every rank (NCCL all-gather; identity at world 1)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=dev)
+    if world == 1:
+        return t.cpu().numpy()[None]
+    out = torch.empty((world, t.numel()), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), t)
+    return out.cpu().numpy()
+
+
+def h2d_probe(dev, world, barrier, mb: int = 256, reps: int = 4):
+    """Plain pinned host -> device copy bandwidth of this rank while EVERY rank copies at the same time: what the host
+    (its DRAM, its PCIe root complexes / switches) can feed all N GPUs at once.  GB/s of this rank."""
+    import torch
+    h = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return reps * (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+def e2e_host(eng, cfg, h_np, B, steps, world, dev, barrier):
+    """vti_process_host with pinned HOST buffers, H2D + K1..K5 + D2H inside the timed region, in two feeding modes:
+    "zero_copy" (frames by DMA, head tensors read in place over PCIe) and "dma" (everything copied).  Per-rank seconds
+    are gathered so that the line can say what each rank's PCIe path delivered."""
+    import torch
+    from vision_textile_inspection_b200._lib import DET_DTYPE, RESULT_DTYPE
+    o_dets = torch.empty((B, cfg.max_det, DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    o_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+    o_res = torch.empty((B, RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    out = (o_dets.numpy().view(DET_DTYPE).reshape(B, cfg.max_det), o_counts.numpy(),
+           o_res.numpy().view(RESULT_DTYPE).reshape(B))
+    modes = {}
+    for mode in ("zero_copy", "dma"):
+        if mode == "dma":
+            os.environ["VTI_NO_ZERO_COPY"] = "1"
+        else:
+            os.environ.pop("VTI_NO_ZERO_COPY", None)
+        for _ in range(2):
+            eng.process_host(*h_np, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.process_host(*h_np, out=out)
+        mine = time.perf_counter() - t0
+        barrier()
+        modes[mode] = _allgather_floats([mine], world, dev)[:, 0]          # seconds per rank
+    os.environ.pop("VTI_NO_ZERO_COPY", None)
+    ed, ec, er = out
+    # bytes that cross PCIe per step and rank.  DMA mode: everything presented.  Zero-copy mode: the frames by DMA + what
+    # the kernels read in place (class planes, 64 box logits per candidate, kept coefficient rows, the union rectangle
+    # of the crop windows of the prototypes; 32-byte sectors), estimated from the records of the last call.
+    presented = sum(a.nbytes for a in h_np)
+    zc = 0
+    for b in range(B):
+        n = int(ec[b])
+        zc += 4 * cfg.nc * cfg.anchors + 32 * 64 * int(er["n_cand"][b]) + 32 * 32 * n
+        if n:
+            bx = ed[b, :n]["box_lb"] * 0.25
+            x0, y0 = np.maximum(np.ceil(bx[:, 0]), 0).min(), np.maximum(np.ceil(bx[:, 1]), 0).min()
+            x1 = np.minimum(np.ceil(bx[:, 2]) - 1, cfg.LW // 4 - 1).max()
+            y1 = np.minimum(np.ceil(bx[:, 3]) - 1, cfg.LH // 4 - 1).max()
+            zc += int(max(y1 - y0 + 1, 0) * (max(x1 - x0 + 1, 0) + 6)) * 32 * 4
+    d2h = o_dets.numel() + 4 * o_counts.numel() + o_res.numel()
+    h2d = {"zero_copy": int(h_np[0].nbytes + zc), "dma": int(presented)}
+    best = min(modes, key=lambda m: modes[m].max())
+    rep = {m: {"frames_per_s": world * B * steps / float(modes[m].max()),
+               "h2d_gbs_per_rank": [round(h2d[m] * steps / float(t) / 1e9, 2) for t in modes[m]],
+               "h2d_gbs_all_ranks": round(sum(h2d[m] * steps / float(t) / 1e9 for t in modes[m]), 2),
+               "h2d_bytes_per_step": h2d[m]} for m in modes}
+    return {"value": rep[best]["frames_per_s"], "mode": best, "h2d_bytes_per_step": h2d[best], "d2h_bytes_per_step": int(d2h),
+            "h2d_dma_bytes_per_step": int(h_np[0].nbytes if best == "zero_copy" else presented),
+            "h2d_zero_copy_bytes_per_step_est": int(zc if best == "zero_copy" else 0),
+            "host_bytes_presented_per_step": int(presented), "steps": steps, "modes": rep}, out
+
+
+def run_cfg5_sharded(args, rank, world, dev, barrier, calib, use_peer):
+    """BASELINE.json configs[4]: a 256-frame synthetic 4K stream SPLIT across the ranks (shard.shard_range), every GPU
+    runs the whole path on its shard, the per-defect records are gathered on rank 0; resident and end to end."""
+    import torch
+    import torch.distributed as dist
+    from vision_textile_inspection_b200 import shard, synth
+    from vision_textile_inspection_b200.engine import EngineConfig, InspectionEngine
+    cfg = synth.CONFIGS["cfg5"]
+    total = args.cfg5_frames
+    lo, hi = shard.shard_range(total, rank, world)
+    B = hi - lo
+    n_unique = min(B, 8)
+    batch = synth.make_batch(cfg, B, seed0=1000 * cfg.cfg_id + lo, n_unique=n_unique)
+    eng = InspectionEngine(EngineConfig.for_workload(cfg, calib, max_batch=B), device=dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = [pin(batch["frames"])] + [pin(l) for l in batch["levels"]] + [pin(batch["coef"]), pin(batch["proto"])]
+    d = [t.to(dev) for t in host]
+    net_in = torch.empty((B, 3, eng.LH, eng.LW), dtype=torch.float32, device=dev)
+    packed, outs = shard.alloc_packed(B, cfg.max_det, dev)
+    peer = None
+    if world > 1 and use_peer:
+        try:
+            peer = shard.PeerGather(packed.numel(), dev)
+        except Exception:                                        # noqa: BLE001
+            peer = None
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+    gathered = torch.empty((world * packed.numel(),), dtype=torch.uint8, device=dev) if world > 1 and peer is None else None
+    graph = eng.capture_step(d[0], d[1], d[2], d[3], d[4], d[5], net_in=net_in, outputs=outs)[0]
+    slot = [0]
+
+    def step():
+        graph.replay()
+        if world > 1:
+            if peer is not None:
+                slot[0] = peer.push(packed)
+                if rank == 0:
+                    peer.consume(slot[0], out=consumed)          # root reads every step, on the stream of the waits
+            else:
+                dist.all_gather_into_tensor(gathered, packed)
+    consumed = torch.empty((world, packed.numel()), dtype=torch.uint8, device=dev) if peer is not None and rank == 0 else None
+    steps = max(2, min(args.steps, 10))
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = float(_allgather_floats([e0.elapsed_time(e1)], world, dev).max())
+    # what reached rank 0 must be every rank's own counts
+    checked = None
+    if world > 1:
+        mine = outs[1].clone()
+        allc = torch.empty((world, B), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allc.view(-1), mine)
+        if rank == 0:
+            got = consumed if peer is not None else gathered.view(world, -1)
+            _, g_counts, _ = shard.unpack_packed(got, B, cfg.max_det)
+            checked = bool(torch.equal(g_counts.view(world, B), allc))
+            if not checked:
+                raise RuntimeError("cfg5_sharded: rank 0 did not receive every rank's records")
+    eng.set_profiling(True)
+    eng.preprocess(d[0], out=net_in)
+    eng.post_measure(d[1], d[2], d[3], d[4], d[5], outputs=outs)
+    stage_ms = eng.stage_ms()
+    eng.set_profiling(False)
+    e2e, _ = e2e_host(eng, cfg, [t.numpy() for t in host], B, max(2, min(args.steps, 4)), world, dev, barrier)
+    sb = stage_bytes(cfg, float(outs[1].float().mean().item()))
+    peak, _ = peaks()
+    return {"workload": cfg.name, "scaling": "strong", "frames_total": total, "frames_per_gpu": B, "unique_frames_per_gpu": n_unique,
+            "value": total * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "gather": "peer memory push, root consumes every step" if peer is not None else ("NCCL all-gather" if world > 1 else "none (1 GPU)"),
+            "gather_checked": checked, "stage_ms": dict(zip(["K1", "K2", "K3", "K4", "K5"], stage_ms)),
+            "frac_of_hbm_roofline_per_gpu": (B * sum(sb.values()) / (ms / steps * 1e-3) / 1e9) / peak,
+            "e2e": e2e}
+
+
 def run_b200(args, cfg, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -265,8 +431,20 @@ def run_b200(args, cfg, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     calib = load_reference_calibration()
+    # One rank = one slice of the host cores: torchrun starts N processes that would otherwise all land on the same
+    # cores for their pinned-buffer copies and launch threads (every GPU of this pool reports the same CPU affinity).
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            affinity = f"{mine[0]}-{mine[-1]} of {len(cores)} cores"
+        except OSError:
+            affinity = None
     B = cfg.batch if args.batch is None else args.batch
-    n_unique = min(B, 8)
+    n_unique = min(B, args.unique)
     batch = synth.make_batch(cfg, B, seed0=1000 * cfg.cfg_id + 100 * rank, n_unique=n_unique)
     eng = InspectionEngine(EngineConfig.for_workload(cfg, calib, max_batch=B), device=dev)
     # --post-streams 2: consecutive batches are independent, so their post stages may overlap -- a second handle (its
@@ -301,6 +479,16 @@ def run_b200(args, cfg, rank, world, local_rank):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # all ranks or none
         if int(flag.item()) == 0:
             peer = None
+    consumed = (torch.empty((world, bufs[0][0].numel()), dtype=torch.uint8, device=dev)
+                if peer is not None and rank == 0 else None)
+    peer_slot = {"last": 0}
+
+    def peer_push(pk):
+        """This rank's records into root's slot; root copies the slot out on the same stream (flow control of the three
+        slots: shard.PeerGather docstring)."""
+        peer_slot["last"] = peer.push(pk)
+        if consumed is not None:
+            peer.consume(peer_slot["last"], out=consumed)
     in_bytes = (d_frames.numel() + 4 * (sum(l.numel() for l in d_lv) + d_coef.numel() + d_proto.numel()))
     out_bytes = 4 * net_in.numel()
 
@@ -351,7 +539,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                 s_gather.wait_stream(cur)
                 with torch.cuda.stream(s_gather):
                     if peer is not None:
-                        peer.push(pk, k)
+                        peer_push(pk)
                     else:
                         dist.all_gather_into_tensor(gathered[k], pk)
                     ev_gather[k] = torch.cuda.Event()
@@ -365,7 +553,7 @@ def run_b200(args, cfg, rank, world, local_rank):
             s_gather.wait_stream(s_posts[k])
             with torch.cuda.stream(s_gather):
                 if peer is not None:
-                    peer.push(pk, k)                           # rank 0 reads peer.gathered(k)
+                    peer_push(pk)                              # rank 0 copies the slot out right behind the waits
                 else:
                     dist.all_gather_into_tensor(gathered[k], pk)   # ranks in frame order; shard.unpack_packed gives the views
                 ev_gather[k] = torch.cuda.Event()
@@ -412,6 +600,18 @@ def run_b200(args, cfg, rank, world, local_rank):
     join()
     e1.record()
     launches = sum(e.launch_count for e in set(engs)) + nodes_per_graph * replays["n"] - l0   # graph kernel nodes count
+    # two more regions of K steps, timed the same way: the spread of the number (the reported value is the FIRST region)
+    extra_ev = []
+    for _ in range(2):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        fork()
+        for _ in range(args.steps):
+            step()
+        join()
+        a1.record()
+        extra_ev.append((a0, a1))
     # The timed region is K steps (a few ms); nvidia-smi samples every 100 ms.  The identical loop keeps running,
     # untimed, until >= 0.5 s of load has been sampled, so "clocks" describes this workload under load.
     fork()
@@ -425,6 +625,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    region_ms = [ms] + [float(_allgather_floats([a0.elapsed_time(a1)], world, dev).max()) for a0, a1 in extra_ev]
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
     gather_checked = None
@@ -435,7 +636,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         ref_all = torch.empty((world, mine.numel()), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(ref_all.view(-1), mine)
         if rank == 0:
-            got = peer.gathered(k_last) if peer is not None else gathered[k_last].view(world, -1)
+            got = consumed if peer is not None else gathered[k_last].view(world, -1)
             _, g_counts, g_results = shard.unpack_packed(got, B, cfg.max_det)
             got_cat = torch.cat([g_counts.view(world, -1).view(torch.uint8).view(world, -1),
                                  g_results.reshape(world, -1)], dim=1)
@@ -454,47 +655,12 @@ def run_b200(args, cfg, rank, world, local_rank):
     res = eng.results_to_numpy(outs[2])
     n_det_mean = float(outs[1].float().mean().item())
 
-    # ---- end to end through the C ABI with HOST (pinned) buffers: H2D + K1..K5 + D2H every step
+    # ---- end to end through the C ABI with HOST (pinned) buffers: H2D + K1..K5 + D2H every step, both feeding modes
     h_np = [host["frames"].numpy()] + [l.numpy() for l in host_lv] + [host["coef"].numpy(), host["proto"].numpy()]
-    from vision_textile_inspection_b200._lib import DET_DTYPE, RESULT_DTYPE
-    o_dets = torch.empty((B, cfg.max_det, DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    o_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-    o_res = torch.empty((B, RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    e2e_out = (o_dets.numpy().view(DET_DTYPE).reshape(B, cfg.max_det), o_counts.numpy(),
-               o_res.numpy().view(RESULT_DTYPE).reshape(B))
     e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(2):
-        eng.process_host(*h_np, out=e2e_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.process_host(*h_np, out=e2e_out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * e2e_steps / e2e_s
-    # DMA-copied bytes: the frames.  The pinned head tensors are read IN PLACE over PCIe (zero copy): K2 reads the class
-    # planes and the 64 box logits of each candidate, K3 the coefficient rows of kept detections, and a fetch kernel the
-    # per-frame union rectangle of the crop windows of the prototypes -- estimated below from the records (32-byte
-    # sector granularity for the scattered reads).
-    h2d_dma = host["frames"].numel()
-    presented = sum(a.nbytes for a in h_np)
-    ed, ec, er = e2e_out
-    zc = 0
-    for b in range(B):
-        n = int(ec[b])
-        zc += 4 * cfg.nc * cfg.anchors + 32 * 64 * int(er["n_cand"][b]) + 32 * 32 * n
-        if n:
-            bx = ed[b, :n]["box_lb"] * 0.25
-            x0, y0 = np.maximum(np.ceil(bx[:, 0]), 0).min(), np.maximum(np.ceil(bx[:, 1]), 0).min()
-            x1 = np.minimum(np.ceil(bx[:, 2]) - 1, cfg.LW // 4 - 1).max()
-            y1 = np.minimum(np.ceil(bx[:, 3]) - 1, cfg.LH // 4 - 1).max()
-            zc += int(max(y1 - y0 + 1, 0) * (max(x1 - x0 + 1, 0) + 6)) * 32 * 4
-    h2d = h2d_dma + zc
-    d2h = o_dets.numel() + 4 * o_counts.numel() + o_res.numel()
+    e2e, e2e_out = e2e_host(eng, cfg, h_np, B, e2e_steps, world, dev, barrier)
+    e2e_value, h2d, d2h = e2e["value"], e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]
+    probe = _allgather_floats([h2d_probe(dev, world, barrier)], world, dev)[:, 0]
     # ---- the same, through the Python drop-in (app.B200Predictor.run) with the backbone's output staying on the device:
     #      only the frames cross PCIe (informational; the headline e2e above also ships the head tensors from the host)
     from vision_textile_inspection_b200.app import B200Predictor
@@ -561,16 +727,54 @@ def run_b200(args, cfg, rank, world, local_rank):
         o_ms = g0.elapsed_time(g1) / args.steps
         other = {"step_form": name, "ms_per_step": o_ms, "frames_per_s": B / (o_ms * 1e-3)}
 
+    # ---- the whole frame with a stand-in network between pre and post (informational, --backbone n|s|m)
+    full_frame = None
+    if args.backbone and world == 1:
+        from vision_textile_inspection_b200.backbone import make_standin_backbone
+        bb = make_standin_backbone(cfg.nc, args.backbone, dev, dtype=torch.bfloat16)
+        pipe = eng.capture_pipeline(bb, B)
+        pipe.frames.copy_(d_frames)
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / n
+        t_full = timed(pipe.replay, max(3, args.steps // 2))
+        g_net = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_net):
+            bb(pipe.net_in, out=pipe.head)
+        t_net = timed(g_net.replay, max(3, args.steps // 2))
+        t_ours = float(sum(stage_ms))
+        full_frame = {"backbone": f"stand-in YOLOv8{args.backbone}-seg topology, random weights, bf16 autocast, channels_last, "
+                                  f"{sum(p.numel() for p in bb.net.parameters()) / 1e6:.2f} M parameters (PyTorch / cuDNN)",
+                      "one_cuda_graph": "K1 -> backbone -> K2 -> K3 -> K4 -> K5, head tensors written in place into the buffers K2-K4 read",
+                      "ms_per_batch_whole_frame": t_full, "ms_per_batch_backbone_alone": t_net,
+                      "ms_per_batch_pre_post_measure_serial": t_ours, "frames_per_s_whole_frame": B / (t_full * 1e-3),
+                      "share_of_pre_post_measure": t_ours / t_full, "head_in_place": bool(pipe.in_place),
+                      "note": "with random weights the head produces few / arbitrary detections: K2-K5 see less work "
+                              "than on the planted tensors of the headline; the share uses the headline's stage times"}
+    # ---- BASELINE configs[4]: the 4K stream split over the ranks (every N > 1; --cfg5 forces it at N = 1)
+    cfg5 = None
+    if (world > 1 or args.cfg5) and not args.no_cfg5:
+        cfg5 = run_cfg5_sharded(args, rank, world, dev, barrier, calib, use_peer=(args.gather == "peer"))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
-    sb = stage_bytes(cfg, n_det_mean)
+    sb = stage_bytes(cfg, n_det_mean)                                      # SURVEY 8d figures (whole_path, roofline)
+    sb_read = stage_bytes(cfg, n_det_mean, float(res["n_cand"].mean()))   # K2 = what it must read
     names = ["K1", "K2", "K3", "K4", "K5"]
     dom = int(np.argmax(stage_ms))
-    achieved = B * sb[names[dom]] / (stage_ms[dom] * 1e-3) / 1e9
+    achieved = B * sb_read[names[dom]] / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -599,7 +803,7 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "net_in": [cfg.LW, cfg.LH], "anchors": cfg.anchors, "undistort": cfg.undistort,
                    "conf": cfg.conf, "iou": cfg.iou, "max_det": cfg.max_det, "mean_dets_per_frame": n_det_mean,
                    "l2": f"inputs+outputs per step {(in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                   "unique_frames": n_unique, "streams": ("one CUDA graph per step: K1 beside K2-K5 on a forked high-priority branch, joined at the end of the graph; the record gather on its own stream (double-buffered records)"
+                   "unique_frames": n_unique, "rank_cpu_affinity": affinity, "streams": ("one CUDA graph per step: K1 beside K2-K5 on a forked high-priority branch, joined at the end of the graph; the record gather on its own stream (double-buffered records)"
                                if graphs is not None else
                                "K1 || K2-K5 on two streams (post at high priority) + the record gather on a third (double-buffered records), joined at the ends of the timed region"),
                    "step_form": "graph" if graphs is not None else "streams",
@@ -611,26 +815,34 @@ def run_b200(args, cfg, rank, world, local_rank):
                    "clock_sampling": "nvidia-smi every 100 ms over the timed steps + an untimed continuation of the same loop",
                    "status_ok_frames": int((res["status"] == 0).sum())},
         "clocks": clocks,
+        "spread": {"ms_per_step_regions": [m / args.steps for m in region_ms],
+                   "rel_spread": (max(region_ms) - min(region_ms)) / min(region_ms),
+                   "note": "three back-to-back timed regions of K steps; `value` is the first"},
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "h2d_dma_bytes_per_step": int(h2d_dma), "h2d_zero_copy_bytes_per_step_est": int(zc),
-                "host_bytes_presented_per_step": int(presented),
-                "api": "vti_process_host: pinned host buffers, 4-chunk copy/compute pipeline; the frames are DMA-copied, "
-                       "the head tensors are read in place over PCIe (zero copy): class planes + candidate box logits "
-                       "(K2), kept coefficient rows (K3), the union rectangle of the crop windows of the prototypes "
-                       "(fetch kernel before K4)"},
+        "e2e": dict(e2e, unit=UNIT,
+                    h2d_probe_gbs_per_rank=[round(float(v), 2) for v in probe],
+                    h2d_probe_gbs_all_ranks=round(float(probe.sum()), 2),
+                    api="vti_process_host: pinned host buffers, 4-chunk copy/compute pipeline.  mode zero_copy: the frames "
+                        "are DMA-copied, the head tensors are read in place over PCIe: class planes + candidate box logits "
+                        "(K2), kept coefficient rows (K3), the union rectangle of the crop windows of the prototypes (fetch "
+                        "kernel before K4).  mode dma: every presented byte is copied.  value = the faster mode at this N; "
+                        "h2d_probe = plain pinned copies issued by all ranks at once (what the host can feed N GPUs)"),
         "e2e_frames_only": e2e_frames_only,
         "latency_single_frame": latency,
         "other_step_form": other,
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": B * sb[names[dom]]},
+                     "algorithmic_bytes_per_launch": B * sb_read[names[dom]]},
         "stage_ms": dict(zip(names, stage_ms)),
-        "stage_gbs": {n: (B * sb[n] / (t * 1e-3) / 1e9 if t > 0 else None) for n, t in zip(names, stage_ms)},
+        "stage_gbs": {n: (B * sb_read[n] / (t * 1e-3) / 1e9 if t > 0 else None) for n, t in zip(names, stage_ms)},
         "whole_path": {"algorithmic_bytes_per_frame": sum(sb.values()),
                        "hbm_roofline_frames_per_s": peak * 1e9 / sum(sb.values()),
                        "frac_of_hbm_roofline": (total_bytes / (ms / args.steps * 1e-3) / 1e9) / peak},
     }
+    if cfg5 is not None:
+        line["cfg5_sharded"] = cfg5
+    if full_frame is not None:
+        line["full_frame"] = full_frame
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
@@ -648,6 +860,12 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unique", type=int, default=64, help="distinct synthetic frames / head tensors per rank (<= batch)")
+    ap.add_argument("--backbone", default=None, choices=["n", "s", "m"],
+                    help="also time the whole frame (K1 -> stand-in YOLOv8-seg network -> K2..K5) as one CUDA graph")
+    ap.add_argument("--cfg5", action="store_true", help="also run the cfg5_sharded block at N = 1")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5_sharded block at N > 1")
+    ap.add_argument("--cfg5-frames", type=int, default=256)
     ap.add_argument("--load-steps", type=int, default=1500, help="untimed continuation for the clock sampler")
     ap.add_argument("--step-form", default="graph", choices=["graph", "streams"],
                     help="graph: one CUDA graph replay per step; streams: the six kernels issued on two streams per step")

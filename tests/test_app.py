@@ -215,3 +215,31 @@ def test_config3_outer_app_returns_the_reference_info_text(tmp_path):
         raise RuntimeError("boom")
     app = A.CheckStitchDistanceApp(str(cp), str(ep), "x.pt", camera_index=None, backbone=broken)
     assert app.process_frame(synth.fabric_frame(cfg, 1))[1] == "Model error"
+
+
+@pytest.mark.gpu
+def test_whole_frame_as_one_cuda_graph_with_standin_backbone(tmp_path):
+    """K1 -> backbone -> K2..K5 captured as ONE CUDA graph; the head writes into the buffers K2 reads
+    (no copy in between); replays are bit-identical and equal the eager path on the same frames."""
+    from vision_textile_inspection_b200.backbone import make_standin_backbone
+    cfg = synth.CONFIGS["native"]
+    cp, ep = write_calibration(tmp_path)
+    torch.backends.cudnn.benchmark = False
+    bb = make_standin_backbone(nc=cfg.nc, scale="n", device="cuda", seed=3)
+    frames = np.stack([synth.fabric_frame(cfg, 40 + i) for i in range(2)])
+    outs = []
+    for graph in (False, True, True):
+        app = A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, backbone=bb, roi=cfg.roi())
+        app.model.use_graph = graph
+        ms = app.process_frames(frames)
+        outs.append([(m.get("error"), m["stitch_count"], m["edge_distance_mm"], m["stitch_width_mm"]) for m in ms])
+        if graph:
+            pipe = next(iter(app.model._pipes.values()))
+            assert pipe.in_place                                          # K2 reads the head's output buffers directly
+            d1 = pipe.outputs[0].clone()
+            pipe.replay(frames)
+            torch.cuda.synchronize()
+            assert torch.equal(d1, pipe.outputs[0])                       # replay is bit-reproducible
+            assert len(app.model._pipes) == 1
+    assert outs[1] == outs[2]
+    assert [o[:2] for o in outs[0]] == [o[:2] for o in outs[1]]          # same decisions eager vs graph

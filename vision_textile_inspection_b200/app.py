@@ -127,6 +127,8 @@ class B200Predictor:
         self.mask_variant = mask_variant      # 0: Ultralytics <= 8.0.x masks (sigmoid, > 0.5); 1: newer (logits, > 0, drop)
         self.extra = {}
         self._engines = {}
+        self.use_graph = False                # True: K1 -> backbone -> K2..K5 of a batch shape run as ONE CUDA graph
+        self._pipes = {}
 
     def engine_for(self, h, w, imgsz, conf, iou, max_det, batch=1) -> InspectionEngine:
         key = (h, w, imgsz, float(conf), float(iou), int(max_det), batch)
@@ -144,6 +146,13 @@ class B200Predictor:
         """frames (B,h,w,3) uint8 host array -> (engine, dets, counts, results, masks) with records on the host."""
         B, h, w = frames.shape[:3]
         eng = self.engine_for(h, w, imgsz, conf, iou, max_det, B)
+        if self.use_graph:
+            key = (id(eng), B, bool(export_masks))
+            pipe = self._pipes.get(key)
+            if pipe is None:
+                pipe = self._pipes[key] = eng.capture_pipeline(self.backbone, B, export_masks)
+            dets, counts, results, masks = pipe.replay(frames)
+            return eng, eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results), masks
         d_frames = torch.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
         net_in = eng.preprocess(d_frames)                                   # K1
         p3, p4, p5, coef, proto = self.backbone(net_in)                     # PyTorch backbone -> raw head tensors

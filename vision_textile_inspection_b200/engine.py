@@ -232,6 +232,10 @@ class InspectionEngine:
                 cur.wait_stream(side)                        # join
         return graph, net_in, outputs
 
+    def capture_pipeline(self, backbone, B: int, export_masks: bool = False) -> "GraphedPipeline":
+        """The WHOLE frame -- K1 -> backbone -> K2 -> K3 -> K4 -> K5 -- for a fixed batch as ONE CUDA graph."""
+        return GraphedPipeline(self, backbone, B, export_masks)
+
     def process_host(self, frames: np.ndarray, p3, p4, p5, coef, proto, want_net_in: bool = False, out=None):
         """End-to-end with HOST numpy buffers (ideally pinned): H2D, K1..K5, D2H.  Returns (dets, counts, results[, net_in])."""
         B = frames.shape[0]
@@ -276,3 +280,58 @@ class InspectionEngine:
         w = masks[b, :n].to(torch.int64) & 0xFFFFFFFF
         bits = (w.unsqueeze(-1) >> torch.arange(32, device=masks.device)) & 1
         return bits.reshape(n, self.LH, self.LW).to(torch.float32)
+
+
+class GraphedPipeline:
+    """K1 -> backbone (PyTorch) -> K2..K5 of a fixed batch captured as ONE CUDA graph.
+
+    Static buffers: `frames` (B,h,w,3) uint8 in, `net_in`, the five head tensors, the record outputs.  The backbone is
+    any callable `net_in -> (p3, p4, p5, coef, proto)`; if it accepts `out=` (backbone.make_standin_backbone does) it
+    writes the head tensors straight into the static buffers K2 / K3 / K4 read -- no copy between the network and the
+    post kernels -- otherwise its results are copied there inside the graph.  `replay(frames)` copies new frames in
+    (host or device tensor) and re-runs the graph; the outputs are overwritten in place."""
+
+    def __init__(self, eng: InspectionEngine, backbone, B: int, export_masks: bool = False):
+        self.eng, self.B = eng, B
+        dev, c = eng.device, eng.cfg
+        self.frames = torch.zeros((B, c.frame_h, c.frame_w, 3), dtype=torch.uint8, device=dev)
+        self.net_in = torch.empty((B, 3, eng.LH, eng.LW), dtype=torch.float32, device=dev)
+        self.head = tuple(torch.empty((B, 64 + c.nc, hh, ww), dtype=torch.float32, device=dev) for hh, ww in eng.level_shapes) + (
+            torch.empty((B, 32, eng.A), dtype=torch.float32, device=dev),
+            torch.empty((B, 32, eng.ph, eng.pw), dtype=torch.float32, device=dev))
+        self.outputs = eng.alloc_outputs(B, export_masks)
+        self.in_place = True
+
+        def body():
+            eng.preprocess(self.frames, out=self.net_in)
+            if self.in_place:
+                got = backbone(self.net_in, out=self.head)
+            else:
+                got = backbone(self.net_in)
+            for dst, src in zip(self.head, got):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src)
+            eng.post_measure(*self.head, outputs=self.outputs)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                          # warm-up off the capture (cuDNN autotuning, lazy loads)
+                try:
+                    body()
+                except TypeError:
+                    self.in_place = False
+                    body()
+                body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                body()
+
+    def replay(self, frames=None):
+        if frames is not None:
+            if isinstance(frames, np.ndarray):
+                frames = torch.from_numpy(np.ascontiguousarray(frames))
+            self.frames.copy_(frames, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
