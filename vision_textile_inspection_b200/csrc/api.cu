@@ -190,7 +190,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
                     h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
-                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units, h->d_proto_bbox};
+                    h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units, h->d_proto_bbox, h->d_dense};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -212,7 +212,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     // nc: K2 packs the class into the top byte of a candidate key; max_batch: K3 packs the frame index into 15 bits
     if (p->nc < 1 || p->nc > 255 || p->max_det < 1 || p->max_det > 1024 || p->max_batch < 1 || p->max_batch > 32767 ||
         p->neighborhood < 0 || p->neighborhood > 7 || (p->variant != 0 && p->variant != 1) ||
-        (p->mask_variant != 0 && p->mask_variant != 1)) {
+        (p->mask_variant != 0 && p->mask_variant != 1) || p->k4_dense < 0 || p->k4_dense > 2) {
         vti_set_error("vti_create: parameter out of range (nc 1..255, max_det 1..1024, max_batch 1..32767, "
                       "neighborhood 0..7, variant 0/1, mask_variant 0/1)");
         return VTI_EINVAL;
@@ -309,6 +309,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
     h->units_per_det = ((g.ph + 1 + VTI_K4_UR - 1) / VTI_K4_UR) * ((g.pw + 1 + VTI_K4_UC - 1) / VTI_K4_UC);
     alloc((void**)&h->d_units, sizeof(uint4) * B * p->max_det * h->units_per_det);
     alloc((void**)&h->d_proto_bbox, sizeof(int4) * B);
+    alloc((void**)&h->d_dense, sizeof(int32_t) * B);
     if (e != cudaSuccess) {
         vti_set_error(std::string("vti_create: cudaMalloc: ") + cudaGetErrorString(e));
         vti_destroy(h);
@@ -392,7 +393,9 @@ extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, 
     mark(h, 2, s);
     if ((rc = vti_launch_k2(h, p3, p4, p5, B, s))) return rc;
     mark(h, 3, s);
-    if ((rc = vti_launch_k3(h, coef, B, dets, counts, masks != nullptr, s))) return rc;
+    // (VTI_ALL_DETS: mask statistics for EVERY kept detection, not only routed stitch / fabric ones -- the dense-overlap
+    //  experiments of tools/k4_dense_bench.py use many classes so that class-offset NMS keeps overlapping boxes)
+    if ((rc = vti_launch_k3(h, coef, B, dets, counts, masks != nullptr || getenv("VTI_ALL_DETS") != nullptr, s))) return rc;
     mark(h, 4, s);
     rc = vti_launch_k4(h, proto, B, dets, counts, masks, s);
     mark(h, 5, s);

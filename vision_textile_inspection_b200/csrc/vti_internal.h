@@ -61,6 +61,7 @@ struct vti_handle {
     uint4* d_units;                                // K4 work units: (frame | fabric << 15 | det << 16, block row | block col << 16,
                                                    //                 cx_lo | cy_lo << 16, cx_hi | cy_hi << 16)
     int units_per_det;                             // capacity per detection slot
+    int32_t* d_dense;                              // [B] 1 = this frame's masks go through the tcgen05 tile form of K4
     int4* d_proto_bbox;                            // [B] union of the crop windows of a frame (prototype pixels K4 reads)
     // ---- host-buffer path
     cudaStream_t own_stream, copy_stream;
