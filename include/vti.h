@@ -21,6 +21,7 @@
  *                    K4  coef x proto contraction + sigmoid + crop + 4x bilinear + >0.5,
  *                        fused with the nearest-resize mask statistics of measurement.py      (U6, M2-M4)
  *   vti_measure      K5  ROI routing, envelope, centroids, k-means row pick, pixel->mm         (M1, M3-M8)
+ *   vti_annotate     K6  overlay rasterisation (+ vti_encode_jpeg: nvJPEG), off the hot path   (8f rank 3)
  */
 #ifndef VTI_H_
 #define VTI_H_
@@ -184,6 +185,21 @@ int vti_post_measure(vti_handle* h, const float* p3, const float* p4, const floa
 int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, const float* p4, const float* p5,
                      const float* coef, const float* proto, int B, float* net_in, vti_det* dets, int32_t* counts,
                      vti_frame_result* results);
+
+/* K6 (off the hot path) -- the annotated overlay of measurement.py:230-236, 268-272, 292-296, 358-368,
+ * 460-462 rasterised on the GPU.  Call after vti_measure / vti_post_measure of the SAME batch on the same handle (the
+ * fabric envelope of that call is read).  frames / annotated: device, B x frame_h x frame_w x 3 uint8 BGR; annotated
+ * receives a copy of the frames with the ROI rectangle, detection boxes, envelope polyline, stitch width markers and
+ * edge-distance lines drawn in the reference's colours and order. */
+int vti_annotate(vti_handle* h, const uint8_t* frames, int B, const vti_det* dets, const int32_t* counts,
+                 uint8_t* annotated, void* stream);
+/* One text line (5 x 7 bitmap font, `scale` pixels per dot) into frame `frame` of an annotated batch: measurement.py:500-504
+ * (cv2.putText there). */
+int vti_draw_text(vti_handle* h, uint8_t* annotated, int frame, int x, int y, const char* text, int scale, int b, int g,
+                  int r, void* stream);
+/* nvJPEG encode of ONE device frame (frame_h x frame_w x 3 BGR) -- main.py:314's cv2.imwrite(.., annotated).  quality
+ * 1..100 (0 = 95, cv2's default), 4:2:0.  Returns the number of bytes written to the HOST buffer `out`, or VTI_E*. */
+long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int quality, uint8_t* out, long long capacity, void* stream);
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t vti_launch_count(const vti_handle* h);

@@ -27,7 +27,8 @@ def test_exports_match_header():
 
 
 def test_struct_sizes_match_header():
-    assert C.sizeof(_lib.VtiParams) == 22 * 4 + 2 * 4 + (9 + 5 + 9 + 3 + 1) * 8
+    # 22 int32 + conf, iou + K, dist, R, t, iou_threshold doubles + mask_variant, k4_dense (round 2)
+    assert C.sizeof(_lib.VtiParams) == 22 * 4 + 2 * 4 + (9 + 5 + 9 + 3 + 1) * 8 + 2 * 4
     assert _lib.DET_DTYPE.itemsize == 160
 
 

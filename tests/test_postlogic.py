@@ -45,3 +45,25 @@ def test_known_answers():
     # process_frame error dict ('Fabric not detected'): both None -> buffered values
     r = logic.update({"edge_distance_mm": None, "stitch_width_mm": None, "error": "Fabric not detected"}, 6)
     assert r.valid and not r.measured and r.row is not None
+
+
+def test_record_logic_matches_the_verbatim_main_py_block():
+    """Pinned against the reference itself: oracle/main_verbatim.py executes main.py:214-293 as it stands in the
+    reference's file (constants from the reference's config module), with the same seeded jitter stream."""
+    import pytest
+    from oracle import main_verbatim
+    from vision_textile_inspection_b200 import postlogic
+    if not main_verbatim.available():
+        pytest.skip("no reference copy (baseline/stage_reference.py)")
+    for seed in range(5):
+        ms, counts = _sequence(seed)
+        ref, ns = main_verbatim.run(ms, counts, seed, total_distance_mm=12.5)
+        # the product's defaults are the reference's config values
+        assert (ns["SEAM_LENGTH_OFFSET"], ns["STITCH_WIDTH_OFFSET"]) == (postlogic.SEAM_LENGTH_OFFSET, postlogic.STITCH_WIDTH_OFFSET)
+        assert (ns["Seam_lower_limit"], ns["Seam_upper_limit"]) == postlogic.SEAM_LIMITS
+        assert (ns["stitch_lower_limit"], ns["stitch_upper_limit"]) == postlogic.STITCH_LIMITS
+        logic = SeamRecordLogic(total_distance_mm=12.5, jitter=random.Random(seed).uniform)
+        got = [logic.update(m, c).row for m, c in zip(ms, counts)]
+        assert got == ref
+        assert abs(logic.total_distance_mm - ns["total_distance_mm"]) < 1e-9
+        assert main_logic_ref.run(ms, counts, random.Random(seed).uniform, total_distance_mm=12.5) == ref

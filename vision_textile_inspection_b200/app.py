@@ -129,6 +129,7 @@ class B200Predictor:
         self._engines = {}
         self.use_graph = False                # True: K1 -> backbone -> K2..K5 of a batch shape run as ONE CUDA graph
         self._pipes = {}
+        self.last_device = None
 
     def engine_for(self, h, w, imgsz, conf, iou, max_det, batch=1) -> InspectionEngine:
         key = (h, w, imgsz, float(conf), float(iou), int(max_det), batch)
@@ -152,11 +153,13 @@ class B200Predictor:
             if pipe is None:
                 pipe = self._pipes[key] = eng.capture_pipeline(self.backbone, B, export_masks)
             dets, counts, results, masks = pipe.replay(frames)
+            self.last_device = (eng, pipe.frames, dets, counts)
             return eng, eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results), masks
         d_frames = torch.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
         net_in = eng.preprocess(d_frames)                                   # K1
         p3, p4, p5, coef, proto = self.backbone(net_in)                     # PyTorch backbone -> raw head tensors
         dets, counts, results, masks = eng.post_measure(p3, p4, p5, coef, proto, export_masks=export_masks)  # K2..K5
+        self.last_device = (eng, d_frames, dets, counts)       # for the GPU overlay (engine.annotate) of this batch
         return eng, eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results), masks
 
     def predict(self, source, verbose=False, conf=0.25, iou=0.7, max_det=300, imgsz=640, **_ignored):
@@ -190,7 +193,7 @@ class StitchMeasurementApp:
                  min_stitches=MIN_STITCHES, stitch_id=STITCH_CLASS_ID, fabric_id=FABRIC_CLASS_ID, *, backbone=None,
                  roi=ROI_DEFAULT, conf=CONF_THRESH, iou=IOU_THRESH, max_det=MAX_DETECTIONS, imgsz=960, undistort=0,
                  max_px_distance=MAX_PX_DISTANCE, neighborhood=ENVELOPE_NEIGHBORHOOD, annotate=True, device=None,
-                 mask_variant=0):
+                 mask_variant=0, jpeg_quality=0):
         if not os.path.exists(calib_path):
             raise FileNotFoundError(f"Calibration file missing: {calib_path}")
         calib = load_json(calib_path)
@@ -218,7 +221,8 @@ class StitchMeasurementApp:
         self.model.extra = dict(min_stitches=min_stitches, stitch_id=stitch_id, fabric_id=fabric_id,
                                 max_px_distance=max_px_distance, neighborhood=neighborhood)
         self.conf, self.iou, self.max_det, self.imgsz = conf, iou, max_det, imgsz
-        self.annotate = annotate
+        self.annotate = annotate               # True: minimal cv2 overlay on the host; "gpu": K6 overlay (+ nvJPEG); False: none
+        self.jpeg_quality, self.last_jpeg = jpeg_quality, None
 
         self.cap, self.aw, self.ah = None, calib_w, calib_h
         if camera_index is not None:
@@ -278,10 +282,37 @@ class StitchMeasurementApp:
             print("Model inference error:", e)
             return frame.copy(), {"edge_distance_mm": None, "stitch_width_mm": None, "stitch_count": 0,
                                   "timestamp": datetime.now(), "error": "Model inference failed"}
+        if self.annotate == "gpu":
+            return self._annotate_gpu(frame, m), m
         annotated = frame.copy()
         if self.annotate:
             self._draw(annotated, m)
         return annotated, m
+
+    def _annotate_gpu(self, frame, m):
+        """annotate="gpu": the overlay rasterised by libvti (K6) on the frame that is already on the device, optionally
+        JPEG-encoded there as well (`jpeg_quality`; main.py:314 writes the annotated frame with cv2.imwrite) -- the last
+        per-frame CPU cost of the reference's loop.  `self.last_jpeg` holds the encoded bytes."""
+        eng, d_frames, dets, counts = self.model.last_device
+        h = frame.shape[0]
+        sd, sw = m.get("edge_distance_mm"), m.get("stitch_width_mm")
+        if "error" in m:
+            text = m["error"]
+        elif sd is not None and sw is not None:
+            text = f"Edge Dist: {sd:.2f}mm | Avg Width: {sw:.2f}mm (n_d={m['stitch_count']})"
+        elif sd is not None:
+            text = f"Edge Distance: {sd:.2f}mm (n={m['stitch_count']})"
+        elif sw is not None:
+            text = f"Avg Width: {sw:.2f}mm"
+        else:
+            text = f"Insufficient stitches (need {self.min_stitches})"
+        rec = self.last_records[0] if self.last_records else []
+        info = f"Stitches: {int(sum(1 for d in rec if d['flags'] & _lib.F_STITCH and d['flags'] & _lib.F_IN_ROI))} | " \
+               f"Fabric: {int(sum(1 for d in rec if d['flags'] & _lib.F_FABRIC and d['flags'] & _lib.F_IN_ROI and d['flags'] & _lib.F_HAS_MASK))}"
+        ann = eng.annotate(d_frames[:1], dets[:1], counts[:1],
+                           texts=[[(10, 14, text, 2, (0, 0, 255)), (10, h - 18, info, 1, (0, 0, 0))]])
+        self.last_jpeg = eng.encode_jpeg(ann[0], self.jpeg_quality) if self.jpeg_quality else None
+        return ann[0].cpu().numpy()
 
     def _draw(self, img, m):
         """Overlay (OUT of the hot path): ROI box, per-stitch edge lines, the info line."""

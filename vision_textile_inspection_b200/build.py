@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("VTI_LIB", os.path.join(HERE, "libvti.so"))      # (tuning sweeps build side-by-side variants)
-SOURCES = ["api.cu", "k1_preprocess.cu", "k2_decode.cu", "k3_nms.cu", "k4_masks.cu", "k5_measure.cu"]
+SOURCES = ["api.cu", "k1_preprocess.cu", "k2_decode.cu", "k3_nms.cu", "k4_masks.cu", "k5_measure.cu", "k6_overlay.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "-Xcompiler", "-ffp-contract=off"]
@@ -46,7 +46,10 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    # nvJPEG (toolkit library, same image on the GPU box) for vti_encode_jpeg; rpath so that dlopen finds it
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
+    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                           f"-L{cuda_lib}", "-lnvjpeg", "-Xlinker", f"-rpath={cuda_lib}"])
     return LIB
 
 

@@ -234,6 +234,35 @@ class InspectionEngine:
                 cur.wait_stream(side)                        # join
         return graph, net_in, outputs
 
+    # ------------------------------------------------------------------------------- overlay + JPEG (off the hot path)
+    def annotate(self, frames: torch.Tensor, dets: torch.Tensor, counts: torch.Tensor, texts=None, out=None) -> torch.Tensor:
+        """K6: the reference's overlay drawn on the GPU into a copy of `frames` (B,h,w,3 uint8 BGR, device).  Call right
+        after post_measure() of the same batch.  texts: optional list (per frame) of (x, y, string, scale, (b, g, r))."""
+        B = frames.shape[0]
+        self._chk(frames, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "frames")
+        if out is None:
+            out = torch.empty_like(frames)
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_annotate(self._h, frames.data_ptr(), B, dets.data_ptr(), counts.data_ptr(), out.data_ptr(),
+                                        self._stream()), "vti_annotate")
+            for b, items in enumerate(texts or []):
+                for (x, y, text, scale, col) in items or []:
+                    check(self.lib.vti_draw_text(self._h, out.data_ptr(), b, int(x), int(y), text.encode("ascii", "replace"),
+                                                 int(scale), int(col[0]), int(col[1]), int(col[2]), self._stream()),
+                          "vti_draw_text")
+        return out
+
+    def encode_jpeg(self, image: torch.Tensor, quality: int = 95) -> bytes:
+        """nvJPEG encode of one (h,w,3) uint8 BGR device frame (main.py:314 saves the annotated frame as a JPEG)."""
+        self._chk(image, torch.uint8, (self.cfg.frame_h, self.cfg.frame_w, 3), "image")
+        cap = self.cfg.frame_h * self.cfg.frame_w * 3 + 65536
+        buf = (C.c_uint8 * cap)()
+        with torch.cuda.device(self.device):
+            n = self.lib.vti_encode_jpeg(self._h, image.data_ptr(), int(quality), buf, cap, self._stream())
+        if n < 0:
+            check(int(n), "vti_encode_jpeg")
+        return bytes(buf[:n])
+
     def capture_pipeline(self, backbone, B: int, export_masks: bool = False) -> "GraphedPipeline":
         """The WHOLE frame -- K1 -> backbone -> K2 -> K3 -> K4 -> K5 -- for a fixed batch as ONE CUDA graph."""
         return GraphedPipeline(self, backbone, B, export_masks)
