@@ -191,22 +191,40 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         }
         if (m00 > 0) {
             f |= VTI_F_HAS_MASK;
-            // Area of the bitmap on the fabric plane (north-star "area"; spec: oracle/measure_port.py defect_area_mm2):
-            // m00 pixels x the plane area of one pixel at the centroid, |dP/du x dP/dv| by central differences.
-            const double cx = (double)dets[k].m10 / (double)m00, cy = (double)dets[k].m01 / (double)m00;
-            double pu0[3], pu1[3], pv0[3], pv1[3];
-            if (pixel_to_world(cam, cx - 0.5, cy, pu0) && pixel_to_world(cam, cx + 0.5, cy, pu1) &&
-                pixel_to_world(cam, cx, cy - 0.5, pv0) && pixel_to_world(cam, cx, cy + 0.5, pv1)) {
-                const double ux = pu1[0] - pu0[0], uy = pu1[1] - pu0[1], uz = pu1[2] - pu0[2];
-                const double vx = pv1[0] - pv0[0], vy = pv1[1] - pv0[1], vz = pv1[2] - pv0[2];
-                const double c0 = uy * vz - uz * vy, c1 = uz * vx - ux * vz, c2 = ux * vy - uy * vx;
-                dets[k].area_mm2 = (double)m00 * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 1e6;
-            }
         } else {
             dets[k].col_min = -1; dets[k].col_max = -1;
         }
         dets[k].flags = f;
         s_flags[k] = f;
+    }
+    // Area of every bitmap on the fabric plane (north-star "area"; spec: oracle/measure_port.py defect_area_mm2): m00 pixels x
+    // the plane area of one pixel at the centroid, |dP/du x dP/dv| by central differences.  The four projections of a
+    // detection run on four neighbouring lanes (fp64 division-heavy: this is the longest per-detection piece of K5).
+    for (int base = 0; base < 4 * n; base += K5_THREADS) {           // warp-uniform trip count (shuffles below)
+        const int t = base + tid, k = t >> 2, j = t & 3;
+        double p[3] = {0.0, 0.0, 0.0};
+        bool ok = false;
+        long long m00 = 0;
+        if (k < n) {
+            m00 = dets[k].m00;
+            if (m00 > 0) {
+                const double cx = (double)dets[k].m10 / (double)m00, cy = (double)dets[k].m01 / (double)m00;
+                ok = pixel_to_world(cam, cx + (j == 0 ? -0.5 : (j == 1 ? 0.5 : 0.0)), cy + (j == 2 ? -0.5 : (j == 3 ? 0.5 : 0.0)), p);
+            }
+        }
+        const int l0 = lane & ~3;
+        double q[4][3];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q[jj][c] = __shfl_sync(0xffffffffu, p[c], l0 + jj);
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (k < n && j == 0 && m00 > 0 && ((okm >> l0) & 0xFu) == 0xFu) {
+            const double ux = q[1][0] - q[0][0], uy = q[1][1] - q[0][1], uz = q[1][2] - q[0][2];
+            const double vx = q[3][0] - q[2][0], vy = q[3][1] - q[2][1], vz = q[3][2] - q[2][2];
+            const double c0 = uy * vz - uz * vy, c1 = uz * vx - ux * vz, c2 = ux * vy - uy * vx;
+            dets[k].area_mm2 = (double)m00 * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 1e6;
+        }
     }
     const int* __restrict__ env = a.env + (size_t)b * a.LW;
     for (int x = tid; x < a.w; x += K5_THREADS) envf[x] = env[a.xmap[x]];   // variant 1 keeps INT_MAX = none for now
