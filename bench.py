@@ -767,6 +767,30 @@ def run_b200(args, cfg, rank, world, local_rank):
                       "share_of_pre_post_measure": t_ours / t_full, "head_in_place": bool(pipe.in_place),
                       "note": "with random weights the head produces few / arbitrary detections: K2-K5 see less work "
                               "than on the planted tensors of the headline; the share uses the headline's stage times"}
+    # ---- compressed ingest (informational, --jpeg): camera MJPEG frames decoded by nvJPEG on the device
+    ingest_jpeg = None
+    if args.jpeg and world == 1:
+        import cv2
+        jp = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for f in batch["frames"]]
+        fr = torch.empty_like(d_frames)
+        for _ in range(2):
+            eng.decode_jpeg_batch(jp, out=fr)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.decode_jpeg_batch(jp, out=fr)
+        torch.cuda.synchronize()
+        dec_s = (time.perf_counter() - t0) / 3
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.decode_jpeg_batch(jp, out=fr)
+            eng.preprocess(fr, out=net_in)
+            eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=outs)
+            outs[1].cpu()
+        tot_s = (time.perf_counter() - t0) / 3
+        ingest_jpeg = {"jpeg_bytes_per_frame": int(np.mean([len(j) for j in jp])), "raw_bytes_per_frame": int(batch["frames"][0].nbytes),
+                       "decode_frames_per_s": B / dec_s, "decode_pre_post_measure_frames_per_s": B / tot_s,
+                       "api": "engine.decode_jpeg_batch (vti_decode_jpeg, nvJPEG, one image per call) -> K1..K5, head tensors on the device"}
     # ---- BASELINE configs[4]: the 4K stream split over the ranks (every N > 1; --cfg5 forces it at N = 1)
     cfg5 = None
     if (world > 1 or args.cfg5) and not args.no_cfg5:
@@ -850,6 +874,8 @@ def run_b200(args, cfg, rank, world, local_rank):
         line["cfg5_sharded"] = cfg5
     if full_frame is not None:
         line["full_frame"] = full_frame
+    if ingest_jpeg is not None:
+        line["ingest_jpeg"] = ingest_jpeg
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
@@ -870,6 +896,7 @@ def main():
     ap.add_argument("--unique", type=int, default=64, help="distinct synthetic frames / head tensors per rank (<= batch)")
     ap.add_argument("--backbone", default=None, choices=["n", "s", "m"],
                     help="also time the whole frame (K1 -> stand-in YOLOv8-seg network -> K2..K5) as one CUDA graph")
+    ap.add_argument("--jpeg", action="store_true", help="also time compressed ingest (nvJPEG decode of JPEG frames on the device)")
     ap.add_argument("--cfg5", action="store_true", help="also run the cfg5_sharded block at N = 1")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5_sharded block at N > 1")
     ap.add_argument("--cfg5-frames", type=int, default=256)

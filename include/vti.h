@@ -78,7 +78,9 @@ typedef struct vti_params {
     int32_t min_stitches;         /* config.py:79 */
     int32_t max_px_distance;      /* config.py:81 (150 in check_stitch_distance.py:38) */
     int32_t neighborhood;         /* config.py:82 */
-    int32_t max_candidates;       /* per-frame NMS candidate capacity, 0 = min(A, 16384) */
+    int32_t max_candidates;       /* per-frame NMS candidate capacity, 0 = min(A, 30000) (Ultralytics' max_nms: no
+                                     overflow is possible below 30000 anchors); more confidence-passing anchors than the
+                                     capacity raise VTI_ST_OVERFLOW (which of them are kept is then unspecified) */
     float conf, iou;              /* predict(conf=..., iou=...) */
     double K[9];                  /* camera_matrix, row major, for frame_w x frame_h */
     double dist[5];               /* k1 k2 p1 p2 k3 */
@@ -200,6 +202,11 @@ int vti_draw_text(vti_handle* h, uint8_t* annotated, int frame, int x, int y, co
 /* nvJPEG encode of ONE device frame (frame_h x frame_w x 3 BGR) -- main.py:314's cv2.imwrite(.., annotated).  quality
  * 1..100 (0 = 95, cv2's default), 4:2:0.  Returns the number of bytes written to the HOST buffer `out`, or VTI_E*. */
 long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int quality, uint8_t* out, long long capacity, void* stream);
+
+/* Compressed frame ingest: nvJPEG decode of ONE JPEG (HOST bytes, e.g. a camera's MJPEG frame that
+ * cv2.VideoCapture would decode on the CPU, main.py:188) into a DEVICE frame buffer (frame_h x frame_w x 3 BGR) that
+ * vti_preprocess reads.  Asynchronous on `stream`. */
+int vti_decode_jpeg(vti_handle* h, const uint8_t* jpeg, long long nbytes, uint8_t* frame, void* stream);
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t vti_launch_count(const vti_handle* h);

@@ -148,3 +148,23 @@ def test_app_gpu_annotation_and_jpeg(tmp_path):
     assert np.all(annotated[cfg.roi()[3], 400] == np.array((144, 238, 144), np.uint8))     # the ROI border
     dec = cv2.imdecode(np.frombuffer(app.last_jpeg, np.uint8), cv2.IMREAD_COLOR)
     assert dec.shape == frame.shape
+
+
+def test_jpeg_ingest_decodes_like_cv2():
+    """camera MJPEG frames decoded by nvJPEG straight into the device buffer K1 reads."""
+    cfg = synth.CONFIGS["cfg2"]
+    eng = InspectionEngine(EngineConfig.for_workload(cfg, helpers.load_calib(), max_batch=2))
+    frames = [synth.fabric_frame(cfg, 70 + i) for i in range(2)]
+    for flags, tol_max, tol_mean in (([cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], 5, 0.5),    # IDCT + colour rounding differ by a few LSB
+                                     ([cv2.IMWRITE_JPEG_QUALITY, 90], 40, 2.0)):           # 4:2:0: chroma upsampling filters differ
+        jp = [cv2.imencode(".jpg", f, flags)[1].tobytes() for f in frames]
+        dev_frames = eng.decode_jpeg_batch(jp)
+        torch.cuda.synchronize()
+        for b in range(2):
+            ref = cv2.imdecode(np.frombuffer(jp[b], np.uint8), cv2.IMREAD_COLOR)
+            d = np.abs(dev_frames[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+            assert d.max() <= tol_max and d.mean() <= tol_mean, (d.max(), d.mean())
+        net_in = eng.preprocess(dev_frames)                                 # and K1 takes it from there
+        assert net_in.shape == (2, 3, eng.LH, eng.LW)
+    with pytest.raises(_lib.VtiError, match="the handle was created for"):
+        eng.decode_jpeg_batch([cv2.imencode(".jpg", frames[0][:100, :100])[1].tobytes()] * 2)

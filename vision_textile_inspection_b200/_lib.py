@@ -57,7 +57,7 @@ EXPORTS = [
     "vti_last_error", "vti_abi_version", "vti_plan_geometry", "vti_plan_resize_taps_x", "vti_plan_resize_taps_y",
     "vti_plan_undistort_map", "vti_plan_nearest_map", "vti_create", "vti_destroy", "vti_get_geometry",
     "vti_preprocess", "vti_postprocess", "vti_measure", "vti_post_measure", "vti_process_host", "vti_launch_count",
-    "vti_set_profiling", "vti_get_stage_ms", "vti_annotate", "vti_draw_text", "vti_encode_jpeg",
+    "vti_set_profiling", "vti_get_stage_ms", "vti_annotate", "vti_draw_text", "vti_encode_jpeg", "vti_decode_jpeg",
 ]
 
 _lib = None
@@ -97,6 +97,7 @@ def load():
     lib.vti_draw_text.argtypes = [vp, vp, i32, i32, i32, C.c_char_p, i32, i32, i32, i32, vp]
     lib.vti_encode_jpeg.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.vti_encode_jpeg.restype = i64
+    lib.vti_decode_jpeg.argtypes = [vp, C.c_char_p, i64, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

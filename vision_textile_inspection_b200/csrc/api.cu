@@ -72,7 +72,7 @@ extern "C" int vti_plan_geometry(int frame_h, int frame_w, int imgsz, int stride
         g->A += g->lvl_h[l] * g->lvl_w[l];
     }
     g->mask_words = g->LW / 32;
-    int cap = max_candidates > 0 ? max_candidates : VTI_CAND_CAP_MAX;
+    int cap = max_candidates > 0 ? max_candidates : VTI_CAND_CAP_DEFAULT;
     if (cap > g->A) cap = g->A;
     if (cap > VTI_CAND_CAP_MAX) cap = VTI_CAND_CAP_MAX;
     g->max_candidates = cap;

@@ -192,8 +192,9 @@ struct Jpeg {
     nvjpegHandle_t handle = nullptr;
     nvjpegEncoderState_t state = nullptr;
     nvjpegEncoderParams_t params = nullptr;
+    nvjpegJpegState_t dec = nullptr;
     std::mutex mu;
-    bool ok = false;
+    bool ok = false, dec_ok = false;
 };
 Jpeg g_jpeg;
 
@@ -252,7 +253,7 @@ extern "C" long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int qu
     std::lock_guard<std::mutex> lock(g_jpeg.mu);
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_jpeg.ok) {
-        if (nvjpegCreateSimple(&g_jpeg.handle) != NVJPEG_STATUS_SUCCESS ||
+        if ((!g_jpeg.handle && nvjpegCreateSimple(&g_jpeg.handle) != NVJPEG_STATUS_SUCCESS) ||
             nvjpegEncoderStateCreate(g_jpeg.handle, &g_jpeg.state, s) != NVJPEG_STATUS_SUCCESS ||
             nvjpegEncoderParamsCreate(g_jpeg.handle, &g_jpeg.params, s) != NVJPEG_STATUS_SUCCESS) {
             vti_set_error("vti_encode_jpeg: nvJPEG initialisation failed");
@@ -287,4 +288,45 @@ extern "C" long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int qu
     }
     VTI_CUDA(cudaStreamSynchronize(s));
     return (long long)len;
+}
+
+// Frame ingest from a compressed camera stream: the camera of the reference delivers MJPEG
+// (cv2.VideoCapture, /root/reference/main.py:188 decodes it on the CPU before process_frame sees the array).  Decodes ONE
+// baseline JPEG (host bytes) with nvJPEG straight into the device frame buffer K1 reads (frame_h x frame_w x 3 BGR), so
+// that the frame crosses PCIe compressed.  The image must have the handle's frame size.
+extern "C" int vti_decode_jpeg(vti_handle* h, const uint8_t* jpeg, long long nbytes, uint8_t* frame, void* stream) {
+    if (!h || !jpeg || nbytes <= 0 || !frame) { vti_set_error("vti_decode_jpeg: bad argument"); return VTI_EINVAL; }
+    std::lock_guard<std::mutex> lock(g_jpeg.mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!g_jpeg.handle && nvjpegCreateSimple(&g_jpeg.handle) != NVJPEG_STATUS_SUCCESS) {
+        vti_set_error("vti_decode_jpeg: nvJPEG initialisation failed");
+        return VTI_ECUDA;
+    }
+    if (!g_jpeg.dec_ok) {
+        if (nvjpegJpegStateCreate(g_jpeg.handle, &g_jpeg.dec) != NVJPEG_STATUS_SUCCESS) {
+            vti_set_error("vti_decode_jpeg: nvjpegJpegStateCreate failed");
+            return VTI_ECUDA;
+        }
+        g_jpeg.dec_ok = true;
+    }
+    int nc = 0, widths[NVJPEG_MAX_COMPONENT], heights[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t css;
+    if (nvjpegGetImageInfo(g_jpeg.handle, jpeg, (size_t)nbytes, &nc, &css, widths, heights) != NVJPEG_STATUS_SUCCESS) {
+        vti_set_error("vti_decode_jpeg: not a JPEG stream nvJPEG can parse");
+        return VTI_EINVAL;
+    }
+    if (widths[0] != h->p.frame_w || heights[0] != h->p.frame_h) {
+        vti_set_error("vti_decode_jpeg: image is " + std::to_string(widths[0]) + "x" + std::to_string(heights[0]) +
+                      ", the handle was created for " + std::to_string(h->p.frame_w) + "x" + std::to_string(h->p.frame_h));
+        return VTI_EINVAL;
+    }
+    nvjpegImage_t dst;
+    std::memset(&dst, 0, sizeof(dst));
+    dst.channel[0] = frame;
+    dst.pitch[0] = (size_t)h->p.frame_w * 3;
+    if (nvjpegDecode(g_jpeg.handle, g_jpeg.dec, jpeg, (size_t)nbytes, NVJPEG_OUTPUT_BGRI, &dst, s) != NVJPEG_STATUS_SUCCESS) {
+        vti_set_error("vti_decode_jpeg: nvjpegDecode failed");
+        return VTI_ECUDA;
+    }
+    return VTI_OK;
 }

@@ -10,7 +10,8 @@
 
 static_assert(sizeof(vti_det) == 160, "vti_det must stay 160 bytes");
 
-#define VTI_CAND_CAP_MAX 16384
+#define VTI_CAND_CAP_MAX 32768      /* hard ceiling of the per-frame candidate list */
+#define VTI_CAND_CAP_DEFAULT 30000  /* Ultralytics' max_nms: with A <= 30000 anchors the list can never overflow */
 #define VTI_K1_TX 128        // K1 output tile
 #define VTI_K1_TY 16
 #define VTI_K4_UR 4          // K4 work unit: interpolation cells per unit, rows x cols

@@ -263,6 +263,18 @@ class InspectionEngine:
             check(int(n), "vti_encode_jpeg")
         return bytes(buf[:n])
 
+    def decode_jpeg_batch(self, jpegs, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Compressed ingest: a list of JPEG byte strings (camera MJPEG frames) -> (B,h,w,3) uint8 BGR frames ON THE DEVICE
+        (nvJPEG), ready for preprocess().  Only the compressed bytes cross PCIe."""
+        B = len(jpegs)
+        if out is None:
+            out = torch.empty((B, self.cfg.frame_h, self.cfg.frame_w, 3), dtype=torch.uint8, device=self.device)
+        self._chk(out, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "out")
+        with torch.cuda.device(self.device):
+            for b, j in enumerate(jpegs):
+                check(self.lib.vti_decode_jpeg(self._h, j, len(j), out[b].data_ptr(), self._stream()), "vti_decode_jpeg")
+        return out
+
     def capture_pipeline(self, backbone, B: int, export_masks: bool = False) -> "GraphedPipeline":
         """The WHOLE frame -- K1 -> backbone -> K2 -> K3 -> K4 -> K5 -- for a fixed batch as ONE CUDA graph."""
         return GraphedPipeline(self, backbone, B, export_masks)
