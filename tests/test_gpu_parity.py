@@ -671,3 +671,21 @@ def test_k4_tcgen05_tile_form_matches_unit_form(name, seeds):
                 assert abs(r0[b][key] - r2[b][key]) <= MM_RTOL * abs(r0[b][key])
     print(f"\ntcgen05 tile form vs unit form ({name}): {flipped} differing mask pixels of {total}")
     assert flipped <= max(2, total // 100000)
+
+
+def test_k1_tma_output_store_is_bit_identical(monkeypatch):
+    """VTI_K1_TMA=1: the output tile leaves through one cp.async.bulk.tensor store instead of per-thread stores."""
+    cfg = synth.CONFIGS["cfg2"]
+    frames = dev(np.stack([synth.fabric_frame(cfg, 2300 + i) for i in range(3)]))
+    eng = make_engine(cfg, 3)
+    ref = eng.preprocess(frames).clone()
+    monkeypatch.setenv("VTI_K1_TMA", "1")
+    got = eng.preprocess(frames)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)
+    cfg1 = synth.CONFIGS["cfg1"]                      # upscale, no undistort: the plain staging path
+    f1 = dev(np.stack([synth.fabric_frame(cfg1, 1300 + i) for i in range(2)]))
+    e1 = make_engine(cfg1, 2)
+    got1 = e1.preprocess(f1)
+    monkeypatch.delenv("VTI_K1_TMA")
+    assert torch.equal(e1.preprocess(f1), got1)

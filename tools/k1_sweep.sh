@@ -9,11 +9,6 @@ build() {  # name flags...
   echo built $name
 }
 rm -rf tools/_variants; mkdir -p tools/_variants
-build A_early3
-build B_early1 -DVTI_K1_EARLY=1
-build C_early2 -DVTI_K1_EARLY=2
-build D_early0 -DVTI_K1_EARLY=0
-build E_early3_reg56 -DVTI_K1_MAXREG=56
-build F_early3_reg64 -DVTI_K1_MAXREG=64
-build G_early0_reg56 -DVTI_K1_EARLY=0 -DVTI_K1_MAXREG=56
+build A_tmaout
+build B_stg -DVTI_K1_TMAOUT=0
 python vision_textile_inspection_b200/build.py --force > /dev/null   # leave the default objects in build/

@@ -22,7 +22,13 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda.h>
+
 #include "vti_internal.h"
+
+// k4_masks.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+bool vti_encode_tmap_f32_3d(CUtensorMap* m, const void* base, unsigned long long d0, unsigned long long d1,
+                            unsigned long long d2, unsigned b0, unsigned b1, unsigned b2);
 
 namespace {
 
@@ -97,7 +103,7 @@ __device__ __forceinline__ unsigned remap_packed(unsigned t00, unsigned t01, uns
 
 template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a) {
-    extern __shared__ __align__(16) unsigned s_dyn[];      // [footprint rows][pitch_u] then the raw box (MODE_RAW)
+    extern __shared__ __align__(128) unsigned s_dyn[];     // [footprint rows][pitch_u] then the raw box (MODE_RAW)
     __shared__ float s_div[256];
     __shared__ int s_rowsrc[MAXROWS];
     __shared__ int s_colsrc[MAXCOLS + 4];
@@ -310,6 +316,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_letterbox_kernel(const K1Args a
 #endif
 #ifndef VTI_K1_DIVFMA    // x / 255 as FMUL + FFMA on split constants (exact for 0..255) instead of a shared-memory table
 #define VTI_K1_DIVFMA 1
+#endif
+#ifndef VTI_K1_TMAOUT    // compile the variant whose output tile leaves through ONE TMA tensor store (run-time opt-in: VTI_K1_TMA=1)
+#define VTI_K1_TMAOUT 1
 #endif
 #ifndef VTI_K1_PADROWS   // strips that contain letterbox padding rows stay on the register-sharing resize path
 #define VTI_K1_PADROWS 1
@@ -559,9 +568,52 @@ __device__ __forceinline__ void resize_strip(const int4* rowtap, unsigned col, u
     }
 }
 
-template <bool REMAP, bool AREA, int LW_T, int RAWP_T>
-__global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const K1FastArgs a) {
-    extern __shared__ __align__(16) unsigned s_dyn[];      // s_und [und_words], then the raw box (REMAP)
+// The resize phase of one thread: RPT output rows of one column, three planes, written to o0 / o0 + plane / o0 + 2 plane
+// with row pitch LW_T (compile time) or LW.  `o0` is either the thread's first pixel in the global output or in the
+// shared-memory output tile that a TMA store ships (row pitch FTX).
+template <bool AREA, int LW_T>
+__device__ __forceinline__ void resize_phase(const K1FastArgs& a, float* __restrict__ o0, size_t plane, int LW, int X, int Y0,
+                                             int j0, int nrows, int c_lo, const unsigned* s_und, const int4* s_rowtap,
+                                             const unsigned char* divb) {
+    const float pad = __uint_as_float(0x3ee4e4e5u);            // float32(114) / 255.0f, the LetterBox border
+    constexpr int RPT = FTY / (FT_THREADS / FTX);          // rows per thread
+    float* __restrict__ o1 = o0 + plane;
+    float* __restrict__ o2 = o1 + plane;
+    int oi = 0;
+    const int rx = X - a.left;
+    const int ry0 = Y0 + j0 - a.top;
+    // rows of this thread's strip that exist in the letterboxed frame, then those that are resized image rows
+    const int n_out = min(RPT, a.LH - (Y0 + j0));
+    if (rx < 0 || rx >= a.new_w || nrows == 0 || ry0 + n_out <= 0 || ry0 >= a.new_h) {     // nothing but padding
+#pragma unroll
+        for (int i = 0; i < RPT; ++i, oi += LW) {
+            if (i < n_out) { store_px<LW_T>(o0, i, oi, pad); store_px<LW_T>(o1, i, oi, pad); store_px<LW_T>(o2, i, oi, pad); }
+        }
+        return;
+    }
+    const int sx = a.tap_x_idx[rx];
+    const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
+    const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
+    const bool full = (ry0 >= 0) && (ry0 + RPT <= a.new_h) && (n_out == RPT);      // warp-uniform
+    if (!AREA && VTI_K1_HSHARE && full) {
+        resize_strip<LW_T, false>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, RPT, pad);
+    } else if (!AREA && VTI_K1_HSHARE && VTI_K1_PADROWS) {
+        resize_strip<LW_T, true>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, n_out, pad);
+    } else {
+        for (int i = 0; i < n_out; ++i, oi += LW) {
+            const int4 rt = s_rowtap[j0 + i];
+            float v0 = pad, v1 = pad, v2 = pad;
+            if (rt.x >= 0) {
+                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
+            }
+            store_px<LW_T>(o0, i, oi, v0); store_px<LW_T>(o1, i, oi, v1); store_px<LW_T>(o2, i, oi, v2);
+        }
+    }
+}
+
+template <bool REMAP, bool AREA, int LW_T, int RAWP_T, bool TMAOUT>
+__global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const K1FastArgs a, const __grid_constant__ CUtensorMap omap) {
+    extern __shared__ __align__(128) unsigned s_dyn[];     // s_und [und_words], then the raw box (REMAP) / the output tile (TMAOUT)
 #if !VTI_K1_DIVFMA
     __shared__ float s_div[256];
 #endif
@@ -625,50 +677,36 @@ __global__ void __launch_bounds__(FT_THREADS, VTI_FT_MINB) k1_fast_kernel(const 
     __syncthreads();
 
     // ----------------------------------------------------------------------------------------------- resize
-    const float pad = __uint_as_float(0x3ee4e4e5u);            // float32(114) / 255.0f, the LetterBox border
     const int X = X0 + (tid & (FTX - 1));
-    if (X >= LW) return;
     constexpr int RPT = FTY / (FT_THREADS / FTX);          // rows per thread
     const int j0 = (tid / FTX) * RPT;
-    const size_t plane = (size_t)a.LH * LW;
-    float* __restrict__ o0 = out + (size_t)(Y0 + j0) * LW + X;       // three plane pointers + one 32-bit row offset
-    float* __restrict__ o1 = o0 + plane;
-    float* __restrict__ o2 = o1 + plane;
-    int oi = 0;
-    const int rx = X - a.left;
-    const int ry0 = Y0 + j0 - a.top;
-    // rows of this thread's strip that exist in the letterboxed frame, then those that are resized image rows
-    const int n_out = min(RPT, a.LH - (Y0 + j0));
-    if (rx < 0 || rx >= a.new_w || nrows == 0 || ry0 + n_out <= 0 || ry0 >= a.new_h) {     // nothing but padding
-#pragma unroll
-        for (int i = 0; i < RPT; ++i, oi += LW) {
-            if (i < n_out) { store_px<LW_T>(o0, i, oi, pad); store_px<LW_T>(o1, i, oi, pad); store_px<LW_T>(o2, i, oi, pad); }
-        }
-        return;
-    }
-    const int sx = a.tap_x_idx[rx];
-    const unsigned a01 = (unsigned)(unsigned short)a.tap_x_a[2 * rx] | ((unsigned)(unsigned short)a.tap_x_a[2 * rx + 1] << 16);
-    const unsigned char* col = reinterpret_cast<const unsigned char*>(s_und) + (sx - c_lo) * 4;   // taps at col, col + 4
 #if VTI_K1_DIVFMA
     const unsigned char* divb = nullptr;
 #else
     const unsigned char* divb = reinterpret_cast<const unsigned char*>(s_div);
 #endif
-    const bool full = (ry0 >= 0) && (ry0 + RPT <= a.new_h) && (n_out == RPT);      // warp-uniform
-    if (!AREA && VTI_K1_HSHARE && full) {
-        resize_strip<LW_T, false>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, RPT, pad);
-    } else if (!AREA && VTI_K1_HSHARE && VTI_K1_PADROWS) {
-        resize_strip<LW_T, true>(s_rowtap + j0, smem_addr(col), a01, divb, o0, o1, o2, LW, n_out, pad);
-    } else {
-        for (int i = 0; i < n_out; ++i, oi += LW) {
-            const int4 rt = s_rowtap[j0 + i];
-            float v0 = pad, v1 = pad, v2 = pad;
-            if (rt.x >= 0) {
-                resize_px<AREA>(col + rt.x, col + rt.y, a01, (unsigned)rt.z, (unsigned)rt.w, divb, v0, v1, v2);
-            }
-            store_at(o0, oi, v0); store_at(o1, oi, v1); store_at(o2, oi, v2);
+    if (TMAOUT) {
+        // The tile's three planes are assembled in shared memory -- in the raw-box region, dead since the barrier above --
+        // and leave through ONE cp.async.bulk.tensor store ({FTX, FTY, 3} box of the [3 B][LH][LW] output; the TMA unit
+        // clips what lies outside the tensor): 24 shared stores per thread at immediate offsets instead of 24 global
+        // stores, and the 24.6 KB of a tile stay off the LSU data pipe (global stores drain at 64 B per cycle there).
+        float* s_out = reinterpret_cast<float*>(s_dyn + a.und_words);
+        if (X < LW)
+            resize_phase<AREA, FTX>(a, s_out + j0 * FTX + (tid & (FTX - 1)), (size_t)FTY * FTX, FTX, X, Y0, j0, nrows, c_lo,
+                                    s_und, s_rowtap, divb);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         :: "l"(reinterpret_cast<unsigned long long>(&omap)), "r"(X0), "r"(Y0), "r"(3 * b), "r"(smem_addr(s_out))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory may go once it has been read
         }
+        return;
     }
+    if (X >= LW) return;
+    resize_phase<AREA, LW_T>(a, out + (size_t)(Y0 + j0) * LW + X, (size_t)a.LH * LW, LW, X, Y0, j0, nrows, c_lo, s_und, s_rowtap, divb);
 }
 
 }  // namespace
@@ -784,34 +822,38 @@ static bool k1_fast_plan(vti_handle* h, const std::vector<int32_t>& xi, const st
 
 // The one place that names every instantiation of the fast kernel: launch == 0 raises each one's dynamic
 // shared-memory limit (plan time), launch == 1 launches the one that matches the handle.
-template <bool REMAP, bool AREA, int LW_T, int RAWP_T>
-static int k1_fast_one(const K1FastArgs* f, int launch, const dim3* grid, size_t smem, cudaStream_t s) {
-    if (!launch) return vti_raise_dyn_smem((const void*)k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T>, smem);
-    k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T><<<*grid, FT_THREADS, smem, s>>>(*f);
+template <bool REMAP, bool AREA, int LW_T, int RAWP_T, bool TMAOUT>
+static int k1_fast_one(const K1FastArgs* f, int launch, const dim3* grid, size_t smem, cudaStream_t s, const CUtensorMap* om) {
+    if (!launch) return vti_raise_dyn_smem((const void*)k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T, TMAOUT>, smem);
+    k1_fast_kernel<REMAP, AREA, LW_T, RAWP_T, TMAOUT><<<*grid, FT_THREADS, smem, s>>>(*f, *om);
     return VTI_OK;
 }
-template <int LW_T>
+template <int LW_T, bool TMAOUT>
 static int k1_fast_lw(bool remap, bool area, int rawp, const K1FastArgs* f, int launch, const dim3* grid, size_t smem,
-                      cudaStream_t s) {
+                      cudaStream_t s, const CUtensorMap* om) {
     int rc = VTI_OK;
     const bool fixed = rawp == K1_RAWP;
-    if (!launch || (remap && area && fixed)) if ((rc = k1_fast_one<true, true, LW_T, K1_RAWP>(f, launch, grid, smem, s))) return rc;
-    if (!launch || (remap && !area && fixed)) if ((rc = k1_fast_one<true, false, LW_T, K1_RAWP>(f, launch, grid, smem, s))) return rc;
-    if (!launch || (remap && area && !fixed)) if ((rc = k1_fast_one<true, true, LW_T, 0>(f, launch, grid, smem, s))) return rc;
-    if (!launch || (remap && !area && !fixed)) if ((rc = k1_fast_one<true, false, LW_T, 0>(f, launch, grid, smem, s))) return rc;
-    if (!launch || (!remap && area)) if ((rc = k1_fast_one<false, true, LW_T, 0>(f, launch, grid, smem, s))) return rc;
-    if (!launch || (!remap && !area)) if ((rc = k1_fast_one<false, false, LW_T, 0>(f, launch, grid, smem, s))) return rc;
+    if (!launch || (remap && area && fixed)) if ((rc = k1_fast_one<true, true, LW_T, K1_RAWP, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
+    if (!launch || (remap && !area && fixed)) if ((rc = k1_fast_one<true, false, LW_T, K1_RAWP, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
+    if (!launch || (remap && area && !fixed)) if ((rc = k1_fast_one<true, true, LW_T, 0, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
+    if (!launch || (remap && !area && !fixed)) if ((rc = k1_fast_one<true, false, LW_T, 0, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
+    if (!launch || (!remap && area)) if ((rc = k1_fast_one<false, true, LW_T, 0, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
+    if (!launch || (!remap && !area)) if ((rc = k1_fast_one<false, false, LW_T, 0, TMAOUT>(f, launch, grid, smem, s, om))) return rc;
     return rc;
 }
+// tma: the output tile leaves through a TMA tensor store (`om` = tensor map of this call's output buffer)
 static int k1_fast_dispatch(vti_handle* h, const K1FastArgs* f, int launch, const dim3* grid, size_t smem,
-                            cudaStream_t s = nullptr) {
+                            cudaStream_t s = nullptr, bool tma = false, const CUtensorMap* om = nullptr) {
     const bool remap = h->k1_mode == MODE_FAST_REMAP, area = h->resize_mode == 2;
     const int LW = h->g.LW, rawp = h->k1_raw_pitch;
     int rc = VTI_OK;
+    if (VTI_K1_TMAOUT && (!launch || tma)) if ((rc = k1_fast_lw<0, true>(remap, area, rawp, f, launch, grid, smem, s, om)) || tma) return rc;
+    static const CUtensorMap none = {};
+    if (!om) om = &none;
     // imgsz 960 and 640 letterboxes (every BASELINE config) get the row pitch as a compile-time constant
-    if (VTI_K1_LWT && (!launch || LW == 960)) if ((rc = k1_fast_lw<960>(remap, area, rawp, f, launch, grid, smem, s))) return rc;
-    if (VTI_K1_LWT && (!launch || LW == 640)) if ((rc = k1_fast_lw<640>(remap, area, rawp, f, launch, grid, smem, s))) return rc;
-    if (!launch || !VTI_K1_LWT || (LW != 960 && LW != 640)) rc = k1_fast_lw<0>(remap, area, rawp, f, launch, grid, smem, s);
+    if (VTI_K1_LWT && (!launch || LW == 960)) if ((rc = k1_fast_lw<960, false>(remap, area, rawp, f, launch, grid, smem, s, om))) return rc;
+    if (VTI_K1_LWT && (!launch || LW == 640)) if ((rc = k1_fast_lw<640, false>(remap, area, rawp, f, launch, grid, smem, s, om))) return rc;
+    if (!launch || !VTI_K1_LWT || (LW != 960 && LW != 640)) rc = k1_fast_lw<0, false>(remap, area, rawp, f, launch, grid, smem, s, om);
     return rc;
 }
 
@@ -828,6 +870,7 @@ int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector
         size_t raw_words = 0;
         if (k1_fast_plan(h, xi, yi, xa, yb, und_ix, und_iy, hdr, lut, pitch_u, rows_u, raw_words, lut_stride, raw_pitch)) {
             const int und_words = (rows_u * pitch_u + 4 + FT_CHUNK - 1) / FT_CHUNK * FT_CHUNK;
+            if (VTI_K1_TMAOUT) raw_words = std::max(raw_words, (size_t)3 * FTY * FTX);      // the output tile reuses the raw-box region
             size_t smem = ((size_t)und_words + raw_words) * 4;
             // Leave room on every SM for the post kernels that run beside K1 (two streams): at most 4 resident K1 CTAs.
             // Measured: 5 CTAs/SM make K1 alone 5 % faster and the whole pre || post step 8 % slower.
@@ -932,7 +975,16 @@ int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cu
         f.und_words = h->k1_und_words; f.lut_stride = h->k1_lut_stride;
         f.raw_pitch = h->k1_raw_pitch;
         dim3 grid((f.LW + FTX - 1) / FTX, (f.LH + FTY - 1) / FTY, B);
-        int rc = k1_fast_dispatch(h, &f, 1, &grid, h->k1_smem, s);
+        // TMA output: a tensor map of THIS call's output buffer ([3 B][LH][LW] float32, box {FTX, FTY, 3}); any buffer that is
+        // not 16-byte aligned (or a toolkit without the encoder) takes the plain-store kernel instead
+        CUtensorMap om;
+        // OPT-IN (VTI_K1_TMA=1): measured on B200 the TMA form is bit-exact and 5 % SLOWER alone (203.6 vs 193.3 us per 64
+        // frames; the same 0.278 ms inside the whole step): the CTA has to stay resident until the TMA unit has read its
+        // 24.6 KB tile out of shared memory, which costs more SM-slot time than the 24 fire-and-forget STG per thread.
+        const bool tma = VTI_K1_TMAOUT && getenv("VTI_K1_TMA") && (reinterpret_cast<uintptr_t>(net_in) & 15) == 0 &&
+                         vti_encode_tmap_f32_3d(&om, net_in, (unsigned long long)f.LW, (unsigned long long)f.LH,
+                                                (unsigned long long)3 * B, FTX, FTY, 3);
+        int rc = k1_fast_dispatch(h, &f, 1, &grid, h->k1_smem, s, tma, tma ? &om : nullptr);
         if (rc) return rc;
         h->launches++;
         VTI_CUDA(cudaGetLastError());

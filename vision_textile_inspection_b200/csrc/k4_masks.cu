@@ -634,6 +634,27 @@ typedef CUresult (*vti_encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint
 static vti_encode_tiled_t g_encode_tiled = nullptr;
 constexpr size_t K4_TMA_SMEM = (size_t)T_WARPS * 2 * TB_BYTES;
 
+// 3-D float32 tensor map (innermost dimension first) with box {b0, b1, b2}; false if the driver entry point is missing
+bool vti_encode_tmap_f32_3d(CUtensorMap* m, const void* base, unsigned long long d0, unsigned long long d1,
+                            unsigned long long d2, unsigned b0, unsigned b1, unsigned b2) {
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<vti_encode_tiled_t>(fn);
+        else
+            cudaGetLastError();
+        if (!g_encode_tiled) return false;
+    }
+    const cuuint64_t gdim[3] = {d0, d1, d2};
+    const cuuint64_t gstr[2] = {d0 * 4, d0 * d1 * 4};
+    const cuuint32_t box[3] = {b0, b1, b2}, estr[3] = {1, 1, 1};
+    return g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int vti_k4_prepare() {
     // cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
     if (!g_encode_tiled) {
