@@ -487,7 +487,7 @@ def test_nms_thousands_of_equal_scores(n_equal):
     assert eng.results_to_numpy(results)["n_cand"][0] == sp["n_cand"]
 
 
-@pytest.mark.parametrize("nc", [3, 5])
+@pytest.mark.parametrize("nc", [3, 5, 200])      # 200: class ids >= 128 (the key's class byte must not sign-extend)
 def test_decode_nms_other_class_counts(nc):
     """nc != 2 (the reference model has two classes): K2's generic class loop (nc > 4) and the unrolled one (nc <= 4),
     first-maximum tie rule and class-offset NMS stay bit-exact against the spec."""
@@ -689,3 +689,22 @@ def test_k1_tma_output_store_is_bit_identical(monkeypatch):
     got1 = e1.preprocess(f1)
     monkeypatch.delenv("VTI_K1_TMA")
     assert torch.equal(e1.preprocess(f1), got1)
+
+
+def test_two_geometries_alive_at_once():
+    """Advisor r1: cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel function, not to a handle -- a later
+    handle with a smaller shared-memory need must not lower the limit under an earlier one (B200Predictor keeps one
+    engine per frame shape).  Two engines with different K1 / K3 footprints, used alternately."""
+    big, small = synth.CONFIGS["cfg2"], synth.CONFIGS["cfg1"]
+    e_big = make_engine(big, 1)                                   # undistort: raw box + footprint, the largest K1 request
+    e_small = make_engine(small, 1, max_candidates=512)           # created later, asks for less
+    f_big, f_small = dev(synth.fabric_frame(big, 1)[None]), dev(synth.fabric_frame(small, 2)[None])
+    ref_big = ultra_ref.preprocess([f_big[0].cpu().numpy()], big.imgsz, undistort=(e_big.cfg.K, e_big.cfg.dist)).numpy()
+    ref_small = ultra_ref.preprocess([f_small[0].cpu().numpy()], small.imgsz).numpy()
+    hd = synth.planted_head(big, 2000)
+    for _ in range(3):
+        assert np.array_equal(e_big.preprocess(f_big).cpu().numpy(), ref_big)
+        assert np.array_equal(e_small.preprocess(f_small).cpu().numpy(), ref_small)
+        _, counts, _, _ = e_big.post_measure(*[dev(l[None]) for l in hd["levels"]], dev(hd["coef"][None]), dev(hd["proto"][None]))
+        assert int(counts[0]) > 10
+    torch.cuda.synchronize()
