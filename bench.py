@@ -773,24 +773,40 @@ def run_b200(args, cfg, rank, world, local_rank):
         import cv2
         jp = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for f in batch["frames"]]
         fr = torch.empty_like(d_frames)
-        for _ in range(2):
-            eng.decode_jpeg_batch(jp, out=fr)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            eng.decode_jpeg_batch(jp, out=fr)
-        torch.cuda.synchronize()
-        dec_s = (time.perf_counter() - t0) / 3
-        t0 = time.perf_counter()
-        for _ in range(3):
-            eng.decode_jpeg_batch(jp, out=fr)
+
+        def _time(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        def _whole(**kw):
+            eng.decode_jpeg_batch(jp, out=fr, **kw)
             eng.preprocess(fr, out=net_in)
             eng.post_measure(d_lv[0], d_lv[1], d_lv[2], d_coef, d_proto, outputs=outs)
             outs[1].cpu()
-        tot_s = (time.perf_counter() - t0) / 3
+
+        one_s = _time(lambda: eng.decode_jpeg_batch(jp, out=fr, one_by_one=True), reps=3)
+        by_lanes = {}
+        for lanes in (1, 2, 4, 8):                      # host threads the batch is split over (vti_decode_jpeg_batch lanes)
+            os.environ["VTI_JPEG_LANES"] = str(lanes)
+            by_lanes[lanes] = B / _time(lambda: eng.decode_jpeg_batch(jp, out=fr))
+        best = max(by_lanes, key=by_lanes.get)
+        os.environ["VTI_JPEG_LANES"] = str(best)
+        dec_s = B / by_lanes[best]
+        tot_s = _time(_whole)
+        os.environ.pop("VTI_JPEG_LANES")
         ingest_jpeg = {"jpeg_bytes_per_frame": int(np.mean([len(j) for j in jp])), "raw_bytes_per_frame": int(batch["frames"][0].nbytes),
+                       "backend": eng.jpeg_backend(),
                        "decode_frames_per_s": B / dec_s, "decode_pre_post_measure_frames_per_s": B / tot_s,
-                       "api": "engine.decode_jpeg_batch (vti_decode_jpeg, nvJPEG, one image per call) -> K1..K5, head tensors on the device"}
+                       "decode_one_by_one_frames_per_s": B / one_s, "lanes": best,
+                       "decode_frames_per_s_by_lanes": {str(k): v for k, v in by_lanes.items()},
+                       "api": "engine.decode_jpeg_batch (vti_decode_jpeg_batch: nvjpegDecodeBatched, JPEG bytes on the host) -> K1..K5, "
+                              "head tensors on the device; one_by_one = vti_decode_jpeg (single-image hybrid decoder)"}
     # ---- BASELINE configs[4]: the 4K stream split over the ranks (every N > 1; --cfg5 forces it at N = 1)
     cfg5 = None
     if (world > 1 or args.cfg5) and not args.no_cfg5:

@@ -208,6 +208,14 @@ long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int quality, uint
  * vti_preprocess reads.  Asynchronous on `stream`. */
 int vti_decode_jpeg(vti_handle* h, const uint8_t* jpeg, long long nbytes, uint8_t* frame, void* stream);
 
+/* The batched form: n JPEG streams (HOST bytes) -> n consecutive device frames, through nvjpegDecodeBatched.  The first
+ * call picks the best nvJPEG backend that accepts the streams -- the NVJPG hardware engines, GPU-assisted Huffman, the
+ * default hybrid (CPU Huffman) -- and vti_jpeg_backend() names it ("nvjpeg-hardware" | "nvjpeg-gpu-hybrid" |
+ * "nvjpeg-hybrid" | "none").  Replaces the per-frame CPU decode inside cv2.VideoCapture.read (main.py:188). */
+int vti_decode_jpeg_batch(vti_handle* h, const uint8_t* const* jpegs, const long long* nbytes, int n, uint8_t* frames,
+                          void* stream);
+const char* vti_jpeg_backend(void);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t vti_launch_count(const vti_handle* h);
 

@@ -158,12 +158,15 @@ def test_jpeg_ingest_decodes_like_cv2():
     for flags, tol_max, tol_mean in (([cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], 5, 0.5),    # IDCT + colour rounding differ by a few LSB
                                      ([cv2.IMWRITE_JPEG_QUALITY, 90], 40, 2.0)):           # 4:2:0: chroma upsampling filters differ
         jp = [cv2.imencode(".jpg", f, flags)[1].tobytes() for f in frames]
-        dev_frames = eng.decode_jpeg_batch(jp)
-        torch.cuda.synchronize()
-        for b in range(2):
-            ref = cv2.imdecode(np.frombuffer(jp[b], np.uint8), cv2.IMREAD_COLOR)
-            d = np.abs(dev_frames[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
-            assert d.max() <= tol_max and d.mean() <= tol_mean, (d.max(), d.mean())
+        for one_by_one in (True, False):          # the single-image decoder and the batched one (best backend of the box)
+            dev_frames = eng.decode_jpeg_batch(jp, one_by_one=one_by_one)
+            torch.cuda.synchronize()
+            for b in range(2):
+                ref = cv2.imdecode(np.frombuffer(jp[b], np.uint8), cv2.IMREAD_COLOR)
+                d = np.abs(dev_frames[b].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+                print(f"jpeg ingest one_by_one={one_by_one} backend={eng.jpeg_backend()} max {d.max()} mean {d.mean():.3f}")
+                assert d.max() <= tol_max and d.mean() <= tol_mean, (one_by_one, eng.jpeg_backend(), d.max(), d.mean())
+        assert eng.jpeg_backend() in ("nvjpeg-hardware", "nvjpeg-gpu-hybrid", "nvjpeg-hybrid")
         net_in = eng.preprocess(dev_frames)                                 # and K1 takes it from there
         assert net_in.shape == (2, 3, eng.LH, eng.LW)
     with pytest.raises(_lib.VtiError, match="the handle was created for"):

@@ -58,6 +58,7 @@ EXPORTS = [
     "vti_plan_undistort_map", "vti_plan_nearest_map", "vti_create", "vti_destroy", "vti_get_geometry",
     "vti_preprocess", "vti_postprocess", "vti_measure", "vti_post_measure", "vti_process_host", "vti_launch_count",
     "vti_set_profiling", "vti_get_stage_ms", "vti_annotate", "vti_draw_text", "vti_encode_jpeg", "vti_decode_jpeg",
+    "vti_decode_jpeg_batch", "vti_jpeg_backend",
 ]
 
 _lib = None
@@ -98,6 +99,9 @@ def load():
     lib.vti_encode_jpeg.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.vti_encode_jpeg.restype = i64
     lib.vti_decode_jpeg.argtypes = [vp, C.c_char_p, i64, vp, vp]
+    lib.vti_decode_jpeg_batch.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(i64), i32, vp, vp]
+    lib.vti_jpeg_backend.argtypes = []
+    lib.vti_jpeg_backend.restype = C.c_char_p
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

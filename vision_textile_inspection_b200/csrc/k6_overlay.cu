@@ -13,8 +13,13 @@
 // Mask contours (:496-499) need the frame-resolution bitmaps the fused path never builds and are not drawn.
 // Layers are separate launches in the reference's drawing order, so overlapping primitives resolve the same way.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include <nvjpeg.h>
 
@@ -329,4 +334,175 @@ extern "C" int vti_decode_jpeg(vti_handle* h, const uint8_t* jpeg, long long nby
         return VTI_ECUDA;
     }
     return VTI_OK;
+}
+
+// ---- batched ingest: the batch through nvjpegDecodeBatched, split over a few host threads ("lanes").  nvJPEG's batched
+// decoder does its bitstream parsing and Huffman-table set-up on the calling thread, so one call per batch leaves the
+// GPU waiting on one host core; each lane owns its nvJPEG handle, state and stream and takes a contiguous slice of the
+// batch, and the caller's stream waits on every lane's event.  Backends are tried once per process, best first: the NVJPG
+// hardware engines (Huffman + IDCT off the SMs), GPU-assisted Huffman, then the default hybrid (CPU Huffman).
+// `vti_jpeg_backend()` names the one that decoded the last batch.
+namespace {
+constexpr int JB_MAX_LANES = 8;
+struct JpegLane {
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t state = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    int backend = -1, batch = 0, device = -1;
+    bool on_device(int dev) {                      // stream + event live as long as the process (or until the device changes)
+        if (device == dev) return true;
+        release();
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        if (done) { cudaEventDestroy(done); done = nullptr; }
+        device = -1;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) return false;
+        device = dev;
+        return true;
+    }
+    void release() {
+        if (state) { nvjpegJpegStateDestroy(state); state = nullptr; }
+        if (handle) { nvjpegDestroy(handle); handle = nullptr; }
+        batch = 0;
+        backend = -1;
+    }
+    bool open(int idx) {
+        release();
+        if (nvjpegCreateEx(kBackendsOf(idx), nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &handle) != NVJPEG_STATUS_SUCCESS) {
+            handle = nullptr;
+            return false;
+        }
+        if (nvjpegJpegStateCreate(handle, &state) != NVJPEG_STATUS_SUCCESS) {
+            state = nullptr;
+            release();
+            return false;
+        }
+        backend = idx;
+        return true;
+    }
+    static nvjpegBackend_t kBackendsOf(int idx) {
+        return idx == 0 ? NVJPEG_BACKEND_HARDWARE : (idx == 1 ? NVJPEG_BACKEND_GPU_HYBRID : NVJPEG_BACKEND_DEFAULT);
+    }
+};
+struct JpegBatch {
+    JpegLane lane[JB_MAX_LANES];
+    nvjpegHandle_t probe = nullptr;    // header parsing only
+    int backend = -1;       // backend index of the last successful batch, -1 = none yet
+    std::mutex mu;
+};
+JpegBatch g_jb;
+const char* const kBackendNames[3] = {"nvjpeg-hardware", "nvjpeg-gpu-hybrid", "nvjpeg-hybrid"};
+
+// one lane decodes images [i0, i1) with backend `idx`; false = this backend cannot take them
+bool jb_lane_decode(JpegLane& L, int idx, int device, const uint8_t* const* jpegs, const size_t* len, nvjpegImage_t* dst, int i0,
+                    int i1) {
+    if (L.backend != idx && !L.open(idx)) return false;
+    const int n = i1 - i0;
+    if (L.batch != n) {
+        if (nvjpegDecodeBatchedInitialize(L.handle, L.state, n, 1, NVJPEG_OUTPUT_BGRI) != NVJPEG_STATUS_SUCCESS) {
+            L.release();
+            return false;
+        }
+        L.batch = n;
+    }
+    if (nvjpegDecodeBatched(L.handle, L.state, (const unsigned char* const*)(jpegs + i0), len + i0, dst + i0, L.stream) !=
+        NVJPEG_STATUS_SUCCESS) {
+        L.release();
+        return false;
+    }
+    return cudaEventRecord(L.done, L.stream) == cudaSuccess;
+}
+}  // namespace
+
+extern "C" const char* vti_jpeg_backend(void) {
+    std::lock_guard<std::mutex> lock(g_jb.mu);
+    return g_jb.backend < 0 ? "none" : kBackendNames[g_jb.backend];
+}
+
+extern "C" int vti_decode_jpeg_batch(vti_handle* h, const uint8_t* const* jpegs, const long long* nbytes, int n, uint8_t* frames,
+                                     void* stream) {
+    if (!h || !jpegs || !nbytes || !frames || n <= 0 || n > h->p.max_batch) {
+        vti_set_error("vti_decode_jpeg_batch: bad argument (1 <= n <= max_batch)");
+        return VTI_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_jb.mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    int device = 0;
+    VTI_CUDA(cudaGetDevice(&device));
+    const size_t frame_bytes = (size_t)h->p.frame_h * h->p.frame_w * 3;
+    std::vector<size_t> len(n);
+    std::vector<nvjpegImage_t> dst(n);
+    for (int i = 0; i < n; ++i) {
+        if (!jpegs[i] || nbytes[i] <= 0) { vti_set_error("vti_decode_jpeg_batch: empty stream in the batch"); return VTI_EINVAL; }
+        len[i] = (size_t)nbytes[i];
+        std::memset(&dst[i], 0, sizeof(nvjpegImage_t));
+        dst[i].channel[0] = frames + (size_t)i * frame_bytes;
+        dst[i].pitch[0] = (size_t)h->p.frame_w * 3;
+    }
+    // geometry check on every stream header (nvjpegGetImageInfo only parses the markers)
+    {
+        if (!g_jb.probe && nvjpegCreateSimple(&g_jb.probe) != NVJPEG_STATUS_SUCCESS) {
+            g_jb.probe = nullptr;
+            vti_set_error("vti_decode_jpeg_batch: nvJPEG initialisation failed");
+            return VTI_ECUDA;
+        }
+        nvjpegHandle_t probe = g_jb.probe;
+        for (int i = 0; i < n; ++i) {
+            int nc = 0, widths[NVJPEG_MAX_COMPONENT], heights[NVJPEG_MAX_COMPONENT];
+            nvjpegChromaSubsampling_t css;
+            if (nvjpegGetImageInfo(probe, jpegs[i], len[i], &nc, &css, widths, heights) != NVJPEG_STATUS_SUCCESS) {
+                vti_set_error("vti_decode_jpeg_batch: stream " + std::to_string(i) + " is not a JPEG nvJPEG can parse");
+                return VTI_EINVAL;
+            }
+            if (widths[0] != h->p.frame_w || heights[0] != h->p.frame_h) {
+                vti_set_error("vti_decode_jpeg_batch: image " + std::to_string(i) + " is " + std::to_string(widths[0]) + "x" +
+                              std::to_string(heights[0]) + ", the handle was created for " + std::to_string(h->p.frame_w) + "x" +
+                              std::to_string(h->p.frame_h));
+                return VTI_EINVAL;
+            }
+        }
+    }
+    const char* force = std::getenv("VTI_JPEG_BACKEND");      // "hardware" | "gpu" | "hybrid": measurement aid
+    int first = 0;
+    if (force) first = !std::strcmp(force, "gpu") ? 1 : (!std::strcmp(force, "hybrid") ? 2 : 0);
+    const char* lanes_env = std::getenv("VTI_JPEG_LANES");
+    int lanes = lanes_env ? std::atoi(lanes_env) : 4;
+    lanes = std::max(1, std::min(std::min(lanes, JB_MAX_LANES), n / 4 > 0 ? n / 4 : 1));      // at least 4 images per lane
+    // the decoded frames must not overtake work already queued on the caller's stream that still reads the buffer
+    cudaEvent_t ready;
+    VTI_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    VTI_CUDA(cudaEventRecord(ready, s));
+    for (int idx = g_jb.backend >= first ? g_jb.backend : first; idx < 3; ++idx) {
+        bool ok[JB_MAX_LANES];
+        std::vector<std::thread> th;
+        for (int l = 0; l < lanes; ++l) {
+            const int i0 = (int)((long long)n * l / lanes), i1 = (int)((long long)n * (l + 1) / lanes);
+            auto work = [&, l, i0, i1]() {
+                ok[l] = false;
+                if (cudaSetDevice(device) != cudaSuccess || !g_jb.lane[l].on_device(device)) return;
+                if (cudaStreamWaitEvent(g_jb.lane[l].stream, ready, 0) != cudaSuccess) return;
+                ok[l] = jb_lane_decode(g_jb.lane[l], idx, device, jpegs, len.data(), dst.data(), i0, i1);
+            };
+            if (lanes == 1) work(); else th.emplace_back(work);
+        }
+        for (auto& t : th) t.join();
+        bool all = true;
+        for (int l = 0; l < lanes; ++l) all = all && ok[l];
+        if (all) {
+            for (int l = 0; l < lanes; ++l) VTI_CUDA(cudaStreamWaitEvent(s, g_jb.lane[l].done, 0));
+            cudaEventDestroy(ready);
+            g_jb.backend = idx;
+            return VTI_OK;
+        }
+        for (int l = 0; l < lanes; ++l) {              // a lane that did start must finish before the buffers are reused
+            if (g_jb.lane[l].stream) cudaStreamSynchronize(g_jb.lane[l].stream);
+            g_jb.lane[l].release();
+        }
+        cudaGetLastError();
+    }
+    cudaEventDestroy(ready);
+    g_jb.backend = -1;
+    vti_set_error("vti_decode_jpeg_batch: no nvJPEG backend decoded the batch");
+    return VTI_ECUDA;
 }

@@ -263,17 +263,28 @@ class InspectionEngine:
             check(int(n), "vti_encode_jpeg")
         return bytes(buf[:n])
 
-    def decode_jpeg_batch(self, jpegs, out: torch.Tensor | None = None) -> torch.Tensor:
+    def decode_jpeg_batch(self, jpegs, out: torch.Tensor | None = None, one_by_one: bool = False) -> torch.Tensor:
         """Compressed ingest: a list of JPEG byte strings (camera MJPEG frames) -> (B,h,w,3) uint8 BGR frames ON THE DEVICE
-        (nvJPEG), ready for preprocess().  Only the compressed bytes cross PCIe."""
+        (nvJPEG, the whole batch in one nvjpegDecodeBatched call on the best backend the box offers; `one_by_one` = the
+        single-image hybrid decoder), ready for preprocess().  Only the compressed bytes cross PCIe."""
         B = len(jpegs)
         if out is None:
             out = torch.empty((B, self.cfg.frame_h, self.cfg.frame_w, 3), dtype=torch.uint8, device=self.device)
         self._chk(out, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "out")
         with torch.cuda.device(self.device):
-            for b, j in enumerate(jpegs):
-                check(self.lib.vti_decode_jpeg(self._h, j, len(j), out[b].data_ptr(), self._stream()), "vti_decode_jpeg")
+            if one_by_one:
+                for b, j in enumerate(jpegs):
+                    check(self.lib.vti_decode_jpeg(self._h, j, len(j), out[b].data_ptr(), self._stream()), "vti_decode_jpeg")
+            else:
+                ptrs = (C.c_char_p * B)(*jpegs)
+                lens = (C.c_int64 * B)(*[len(j) for j in jpegs])
+                check(self.lib.vti_decode_jpeg_batch(self._h, ptrs, lens, B, out.data_ptr(), self._stream()),
+                      "vti_decode_jpeg_batch")
         return out
+
+    def jpeg_backend(self) -> str:
+        """Which nvJPEG backend decoded the last batch ("nvjpeg-hardware" | "nvjpeg-gpu-hybrid" | "nvjpeg-hybrid" | "none")."""
+        return self.lib.vti_jpeg_backend().decode()
 
     def capture_pipeline(self, backbone, B: int, export_masks: bool = False) -> "GraphedPipeline":
         """The WHOLE frame -- K1 -> backbone -> K2 -> K3 -> K4 -> K5 -- for a fixed batch as ONE CUDA graph."""
