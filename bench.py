@@ -283,11 +283,12 @@ def h2d_probe(dev, world, barrier, mb: int = 256, reps: int = 4):
     return reps * (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
-def e2e_host(eng, cfg, h_np, B, steps, world, dev, barrier):
+def e2e_host(eng, cfg, h_np, B, steps, world, dev, barrier, yuyv=False):
     """vti_process_host with pinned HOST buffers, H2D + K1..K5 + D2H inside the timed region, in two feeding modes:
     "zero_copy" (frames by DMA, head tensors read in place over PCIe) and "dma" (everything copied).  Per-rank seconds
     are gathered so that the line can say what each rank's PCIe path delivered."""
     import torch
+    from vision_textile_inspection_b200 import synth as synth_mod
     from vision_textile_inspection_b200._lib import DET_DTYPE, RESULT_DTYPE
     o_dets = torch.empty((B, cfg.max_det, DET_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
     o_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
@@ -295,21 +296,27 @@ def e2e_host(eng, cfg, h_np, B, steps, world, dev, barrier):
     out = (o_dets.numpy().view(DET_DTYPE).reshape(B, cfg.max_det), o_counts.numpy(),
            o_res.numpy().view(RESULT_DTYPE).reshape(B))
     modes = {}
-    for mode in ("zero_copy", "dma"):
+    # camera-native frames: the same scenes as packed YUV 4:2:2, converted on the device by K0
+    yuyv_t = torch.from_numpy(np.stack([synth_mod.bgr_to_yuyv(f) for f in h_np[0][:min(B, 8)]])).pin_memory() if yuyv else None
+    if yuyv_t is not None and B > yuyv_t.shape[0]:
+        yuyv_t = yuyv_t.repeat((B + yuyv_t.shape[0] - 1) // yuyv_t.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+    for mode in ("zero_copy", "dma") + (("yuyv_zero_copy",) if yuyv_t is not None else ()):
         if mode == "dma":
             os.environ["VTI_NO_ZERO_COPY"] = "1"
         else:
             os.environ.pop("VTI_NO_ZERO_COPY", None)
+        args_np = h_np if mode != "yuyv_zero_copy" else [yuyv_t.numpy()] + list(h_np[1:])
         for _ in range(2):
-            eng.process_host(*h_np, out=out)
+            eng.process_host(*args_np, out=out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            eng.process_host(*h_np, out=out)
+            eng.process_host(*args_np, out=out)
         mine = time.perf_counter() - t0
         barrier()
         modes[mode] = _allgather_floats([mine], world, dev)[:, 0]          # seconds per rank
     os.environ.pop("VTI_NO_ZERO_COPY", None)
+    yuyv_modes = {m: modes.pop(m) for m in list(modes) if m.startswith("yuyv")}
     ed, ec, er = out
     # bytes that cross PCIe per step and rank.  DMA mode: everything presented.  Zero-copy mode: the frames by DMA + what
     # the kernels read in place (class planes, 64 box logits per candidate, kept coefficient rows, the union rectangle
@@ -332,7 +339,18 @@ def e2e_host(eng, cfg, h_np, B, steps, world, dev, barrier):
                "h2d_gbs_per_rank": [round(h2d[m] * steps / float(t) / 1e9, 2) for t in modes[m]],
                "h2d_gbs_all_ranks": round(sum(h2d[m] * steps / float(t) / 1e9 for t in modes[m]), 2),
                "h2d_bytes_per_step": h2d[m]} for m in modes}
-    return {"value": rep[best]["frames_per_s"], "mode": best, "h2d_bytes_per_step": h2d[best], "d2h_bytes_per_step": int(d2h),
+    ingest = None
+    if yuyv_modes:
+        t = yuyv_modes["yuyv_zero_copy"]
+        nb = int(yuyv_t.numel() + zc)
+        ingest = {"frames_per_s": world * B * steps / float(t.max()), "h2d_bytes_per_step": nb,
+                  "h2d_gbs_per_rank": [round(nb * steps / float(x) / 1e9, 2) for x in t],
+                  "frame_bytes": int(yuyv_t.numel() // B), "bgr_frame_bytes": int(h_np[0].nbytes // B),
+                  "api": "vti_process_host_yuyv: camera-native packed YUV 4:2:2 host frames (what a V4L2 camera delivers "
+                         "before cv2.VideoCapture.read() converts them), K0 converts on the device in front of K1; head "
+                         "tensors zero-copy as in the headline mode.  Informational: the headline e2e stays on BGR frames, "
+                         "the reference's process_frame input"}
+    return {"value": rep[best]["frames_per_s"], "mode": best, **({"ingest_yuyv": ingest} if ingest else {}), "h2d_bytes_per_step": h2d[best], "d2h_bytes_per_step": int(d2h),
             "h2d_dma_bytes_per_step": int(h_np[0].nbytes if best == "zero_copy" else presented),
             "h2d_zero_copy_bytes_per_step_est": int(zc if best == "zero_copy" else 0),
             "host_bytes_presented_per_step": int(presented), "steps": steps, "modes": rep}, out
@@ -665,7 +683,7 @@ def run_b200(args, cfg, rank, world, local_rank):
     # ---- end to end through the C ABI with HOST (pinned) buffers: H2D + K1..K5 + D2H every step, both feeding modes
     h_np = [host["frames"].numpy()] + [l.numpy() for l in host_lv] + [host["coef"].numpy(), host["proto"].numpy()]
     e2e_steps = max(2, min(args.steps, 10))
-    e2e, e2e_out = e2e_host(eng, cfg, h_np, B, e2e_steps, world, dev, barrier)
+    e2e, e2e_out = e2e_host(eng, cfg, h_np, B, e2e_steps, world, dev, barrier, yuyv=cfg.frame_w % 2 == 0)
     e2e_value, h2d, d2h = e2e["value"], e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]
     probe = _allgather_floats([h2d_probe(dev, world, barrier)], world, dev)[:, 0]
     # ---- the same, through the Python drop-in (app.B200Predictor.run) with the backbone's output staying on the device:

@@ -199,6 +199,18 @@ int vti_annotate(vti_handle* h, const uint8_t* frames, int B, const vti_det* det
  * (cv2.putText there). */
 int vti_draw_text(vti_handle* h, uint8_t* annotated, int frame, int x, int y, const char* text, int scale, int b, int g,
                   int r, void* stream);
+/* K0 -- camera-native frame ingest.  The reference opens its camera without a FOURCC
+ * (measurement.py:22-38), so OpenCV's V4L2 backend negotiates packed YUV 4:2:2 ("YUYV"/"YUY2", 2 bytes per pixel) and
+ * converts every frame to BGR on the CPU inside cap.read() (main.py:188).  vti_ingest_yuyv does that conversion on the
+ * device, bit-exact against cv2.cvtColor(.., COLOR_YUV2BGR_YUY2): yuyv = B x frame_h x frame_w x 2 bytes (device,
+ * 4-byte aligned, frame_w even) -> frames = B x frame_h x frame_w x 3 BGR (device), ready for vti_preprocess. */
+int vti_ingest_yuyv(vti_handle* h, const uint8_t* yuyv, int B, uint8_t* frames, void* stream);
+/* vti_process_host with the frames as the camera delivered them (HOST YUYV bytes): 2/3 of the BGR bytes cross PCIe,
+ * K0 converts in front of K1.  Everything else as vti_process_host. */
+int vti_process_host_yuyv(vti_handle* h, const uint8_t* yuyv, const float* p3, const float* p4, const float* p5,
+                          const float* coef, const float* proto, int B, float* net_in, vti_det* dets, int32_t* counts,
+                          vti_frame_result* results);
+
 /* nvJPEG encode of ONE device frame (frame_h x frame_w x 3 BGR) -- main.py:314's cv2.imwrite(.., annotated).  quality
  * 1..100 (0 = 95, cv2's default), 4:2:0.  Returns the number of bytes written to the HOST buffer `out`, or VTI_E*. */
 long long vti_encode_jpeg(vti_handle* h, const uint8_t* image, int quality, uint8_t* out, long long capacity, void* stream);

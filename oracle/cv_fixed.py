@@ -172,3 +172,25 @@ def scale_K(K, w: int, h: int, calib_w: int = 1280, calib_h: int = 960) -> np.nd
     """Intrinsics for a frame size other than the calibration size (SURVEY 7 'Frame sizes != calibration size')."""
     S = np.diag([w / calib_w, h / calib_h, 1.0])
     return S @ np.asarray(K, np.float64)
+
+
+# ---- camera-native ingest: packed YUV 4:2:2 -> BGR (OpenCV modules/imgproc/src/color_yuv.simd.hpp, YUV422toRGB8Invoker /
+# uvToRGBuv / yRGBuvToRGBA with the ITU-R BT.601 constants below; what cv2.VideoCapture.read() applies to a YUYV camera
+# stream before /root/reference/main.py:188 hands the frame to process_frame).  Pinned in tests/test_oracle_cv.py against
+# cv2.cvtColor(.., COLOR_YUV2BGR_YUY2) over every (Y, U, V) triple.
+ITUR_BT_601_CY, ITUR_BT_601_CUB, ITUR_BT_601_CUG = 1220542, 2116026, -409993
+ITUR_BT_601_CVG, ITUR_BT_601_CVR, ITUR_BT_601_SHIFT = -852492, 1673527, 20
+
+
+def yuyv_to_bgr(yuyv: np.ndarray) -> np.ndarray:
+    """(h, w, 2) uint8 packed Y0 U Y1 V -> (h, w, 3) uint8 BGR, bit-exact cv2.cvtColor(yuyv, cv2.COLOR_YUV2BGR_YUY2)."""
+    assert yuyv.dtype == np.uint8 and yuyv.ndim == 3 and yuyv.shape[2] == 2 and yuyv.shape[1] % 2 == 0
+    y = yuyv[:, :, 0].astype(np.int64)
+    u = np.repeat(yuyv[:, 0::2, 1].astype(np.int64), 2, axis=1) - 128
+    v = np.repeat(yuyv[:, 1::2, 1].astype(np.int64), 2, axis=1) - 128
+    half = 1 << (ITUR_BT_601_SHIFT - 1)
+    yy = np.maximum(0, y - 16) * ITUR_BT_601_CY
+    b = (yy + half + ITUR_BT_601_CUB * u) >> ITUR_BT_601_SHIFT
+    g = (yy + half + ITUR_BT_601_CVG * v + ITUR_BT_601_CUG * u) >> ITUR_BT_601_SHIFT
+    r = (yy + half + ITUR_BT_601_CVR * v) >> ITUR_BT_601_SHIFT
+    return np.clip(np.stack([b, g, r], -1), 0, 255).astype(np.uint8)

@@ -708,3 +708,45 @@ def test_two_geometries_alive_at_once():
         _, counts, _, _ = e_big.post_measure(*[dev(l[None]) for l in hd["levels"]], dev(hd["coef"][None]), dev(hd["proto"][None]))
         assert int(counts[0]) > 10
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------------------ K0
+def test_k0_yuyv_ingest_bit_exact_and_host_path(calib):
+    """Camera-native ingest: K0 = cv2.cvtColor(.., COLOR_YUV2BGR_YUY2) bit for bit -- every (Y, U, V)
+    triple, random frames, an even-but-not-multiple-of-4 width (the 2-pixel kernel) -- and vti_process_host_yuyv gives the
+    records vti_process_host gives on the frames cv2 decodes from the same bytes."""
+    u, v = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    cases = []
+    img = np.empty((65536, 256, 2), np.uint8)                   # all 2^24 triples: run = (U, V), position in the run = Y
+    img[..., 0] = np.arange(256, dtype=np.uint8)
+    img[:, 0::2, 1] = u.reshape(-1, 1)
+    img[:, 1::2, 1] = v.reshape(-1, 1)
+    cases.append(img.reshape(16, 1024, 1024, 2))                # as 16 frames of 1024 x 1024 (4 runs per row)
+    rng = np.random.default_rng(11)
+    cases.append(rng.integers(0, 256, (3, 720, 1280, 2), dtype=np.uint8))
+    cases.append(rng.integers(0, 256, (3, 33, 70, 2), dtype=np.uint8))      # 3 * 33 * 70 pixels: not a multiple of 4
+    for yuyv in cases:
+        B, h, w, _ = yuyv.shape
+        K = cv_fixed.scale_K(np.array(calib["camera_matrix"]), w, h)
+        eng = InspectionEngine(EngineConfig(frame_h=h, frame_w=w, K=K, dist=np.array(calib["dist_coeffs"]), R=np.eye(3),
+                                            t=np.array([0, 0, 0.1]), imgsz=960, max_batch=B, roi=(0, 0, 0, 0, 0)))
+        got = eng.ingest_yuyv(dev(yuyv)).cpu().numpy()
+        for b in range(B):
+            assert np.array_equal(got[b], cv2.cvtColor(yuyv[b], cv2.COLOR_YUV2BGR_YUY2)), (h, w, b)
+    assert np.array_equal(cv_fixed.yuyv_to_bgr(cases[1][0]), cv2.cvtColor(cases[1][0], cv2.COLOR_YUV2BGR_YUY2))
+
+    cfg = synth.CONFIGS["cfg2"]
+    B = 5
+    batch = synth.make_batch(cfg, B, seed0=2000)
+    yuyv = np.stack([synth.bgr_to_yuyv(f) for f in batch["frames"]])
+    bgr = np.stack([cv2.cvtColor(y, cv2.COLOR_YUV2BGR_YUY2) for y in yuyv])
+    eng = make_engine(cfg, B)
+    heads = (*batch["levels"], batch["coef"], batch["proto"])
+    d1, c1, r1, n1 = eng.process_host(yuyv, *heads, want_net_in=True)
+    d2, c2, r2, n2 = eng.process_host(bgr, *heads, want_net_in=True)
+    assert np.array_equal(n1, n2) and np.array_equal(c1, c2) and r1.tobytes() == r2.tobytes()
+    for b in range(B):
+        assert d1[b, :c1[b]].tobytes() == d2[b, :c2[b]].tobytes()
+    with pytest.raises(ValueError):
+        eng.process_host(yuyv[:, :, :, :1], *heads)
+

@@ -40,3 +40,29 @@ def test_undistort_bit_exact(h, w, calib):
     dist = np.array(calib["dist_coeffs"])
     img = np.random.default_rng(h + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
     assert np.array_equal(cv2.undistort(img, K, dist), F.undistort_u8(img, K, dist))
+
+
+def test_yuyv_to_bgr_bit_exact_over_every_triple():
+    """K0's spec (camera-native YUYV ingest) against the real cv2.cvtColor: every (Y, U, V) triple, both
+    pixel positions of a chroma pair, plus random frames."""
+    u, v = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    img = np.empty((65536, 256, 2), np.uint8)                 # row = (U, V), columns = Y (pairs (2k, 2k+1) share the chroma)
+    img[:, :, 0] = np.arange(256, dtype=np.uint8)[None, :]
+    img[:, 0::2, 1] = u.reshape(-1, 1)
+    img[:, 1::2, 1] = v.reshape(-1, 1)
+    assert np.array_equal(cv2.cvtColor(img, cv2.COLOR_YUV2BGR_YUY2), F.yuyv_to_bgr(img))
+    rng = np.random.default_rng(5)
+    for h, w in ((720, 1280), (3, 2), (17, 6)):
+        img = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        assert np.array_equal(cv2.cvtColor(img, cv2.COLOR_YUV2BGR_YUY2), F.yuyv_to_bgr(img))
+
+
+def test_camera_stand_in_round_trip_is_close():
+    """bgr_to_yuyv (the test / bench camera stand-in) followed by the cv2 decode gives back the frame up to 4:2:2 chroma
+    loss -- a sanity check that the synthetic YUYV frames still look like the scene the head tensors were planted for."""
+    from vision_textile_inspection_b200 import synth
+    frame = synth.fabric_frame(synth.CONFIGS["cfg2"], 7)
+    back = F.yuyv_to_bgr(synth.bgr_to_yuyv(frame))
+    d = np.abs(back.astype(np.int32) - frame.astype(np.int32))
+    assert d.mean() < 3.0
+

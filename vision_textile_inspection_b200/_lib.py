@@ -58,7 +58,7 @@ EXPORTS = [
     "vti_plan_undistort_map", "vti_plan_nearest_map", "vti_create", "vti_destroy", "vti_get_geometry",
     "vti_preprocess", "vti_postprocess", "vti_measure", "vti_post_measure", "vti_process_host", "vti_launch_count",
     "vti_set_profiling", "vti_get_stage_ms", "vti_annotate", "vti_draw_text", "vti_encode_jpeg", "vti_decode_jpeg",
-    "vti_decode_jpeg_batch", "vti_jpeg_backend",
+    "vti_decode_jpeg_batch", "vti_jpeg_backend", "vti_ingest_yuyv", "vti_process_host_yuyv",
 ]
 
 _lib = None
@@ -90,6 +90,8 @@ def load():
     lib.vti_measure.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.vti_post_measure.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.vti_process_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.vti_process_host_yuyv.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.vti_ingest_yuyv.argtypes = [vp, vp, i32, vp, vp]
     lib.vti_launch_count.argtypes = [vp]
     lib.vti_launch_count.restype = i64
     lib.vti_set_profiling.argtypes = [vp, i32]

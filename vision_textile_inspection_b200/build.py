@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("VTI_LIB", os.path.join(HERE, "libvti.so"))      # (tuning sweeps build side-by-side variants)
-SOURCES = ["api.cu", "k1_preprocess.cu", "k2_decode.cu", "k3_nms.cu", "k4_masks.cu", "k5_measure.cu", "k6_overlay.cu"]
+SOURCES = ["api.cu", "k0_ingest.cu", "k1_preprocess.cu", "k2_decode.cu", "k3_nms.cu", "k4_masks.cu", "k5_measure.cu", "k6_overlay.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
           "-Xcompiler", "-ffp-contract=off"]

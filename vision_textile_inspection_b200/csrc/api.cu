@@ -189,7 +189,7 @@ extern "C" void vti_destroy(vti_handle* h) {
                     h->lutY.pc, h->lutY.ps, h->lutY.prev_last, h->lutY.next_first, h->lutX.pc, h->lutX.ps,
                     h->lutX.prev_last, h->lutX.next_first,
                     h->d_cand_count, h->d_cand_key, h->d_cand_box, h->d_det_coef, h->d_env, h->d_env_frame, h->d_flags,
-                    h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
+                    h->d_yuyv, h->d_frames, h->d_net_in, h->d_p[0], h->d_p[1], h->d_p[2], h->d_coef, h->d_proto, h->d_dets,
                     h->d_counts, h->d_results, h->d_k1_tiles, h->d_k1_lut, h->d_units, h->d_proto_bbox, h->d_dense};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -446,16 +446,28 @@ static int ensure_staging(vti_handle* h) {
     return VTI_OK;
 }
 
-extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, const float* p4, const float* p5,
-                                const float* coef, const float* proto, int B, float* net_in, vti_det* dets,
-                                int32_t* counts, vti_frame_result* results) {
+extern "C" int vti_ingest_yuyv(vti_handle* h, const uint8_t* yuyv, int B, uint8_t* frames, void* stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!yuyv || !frames) { vti_set_error("vti_ingest_yuyv: null buffer"); return VTI_EINVAL; }
+    if (h->p.frame_w & 1) { vti_set_error("vti_ingest_yuyv: packed 4:2:2 needs an even frame width"); return VTI_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(yuyv) & 3)) { vti_set_error("vti_ingest_yuyv: the YUYV buffer must be 4-byte aligned"); return VTI_EINVAL; }
+    return vti_launch_k0_yuyv(h, yuyv, B, frames, (cudaStream_t)stream);
+}
+
+// fmt 0: BGR frames (3 bytes per pixel); 1: camera-native YUYV (2 bytes per pixel, converted by K0 on the device)
+static int process_host_impl(vti_handle* h, const uint8_t* frames, int fmt, const float* p3, const float* p4, const float* p5,
+                             const float* coef, const float* proto, int B, float* net_in, vti_det* dets,
+                             int32_t* counts, vti_frame_result* results) {
     int rc = check_batch(h, B);
     if (rc) return rc;
     if (!frames || !p3 || !p4 || !p5 || !coef || !proto || !dets || !counts || !results) {
         vti_set_error("vti_process_host: null buffer");
         return VTI_EINVAL;
     }
+    if (fmt == 1 && (h->p.frame_w & 1)) { vti_set_error("vti_process_host_yuyv: packed 4:2:2 needs an even frame width"); return VTI_EINVAL; }
     if ((rc = ensure_staging(h))) return rc;
+    if (fmt == 1 && !h->d_yuyv) VTI_CUDA(cudaMalloc((void**)&h->d_yuyv, (size_t)h->p.max_batch * h->p.frame_h * h->p.frame_w * 2));
     const vti_geometry& g = h->g;
     cudaStream_t s = h->own_stream, cs = h->copy_stream;
     const float* hp[3] = {p3, p4, p5};
@@ -464,6 +476,7 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     // one chunk of compute.
     const int nchunk = B < 4 ? 1 : 4;
     const size_t fsz = (size_t)h->p.frame_h * h->p.frame_w * 3, nsz = (size_t)3 * g.LH * g.LW;
+    const size_t ysz = (size_t)h->p.frame_h * h->p.frame_w * 2;
     size_t lsz[3];
     for (int l = 0; l < 3; ++l) lsz[l] = (size_t)(64 + h->p.nc) * g.lvl_h[l] * g.lvl_w[l];
     const size_t csz = (size_t)VTI_NM * g.A, psz = (size_t)VTI_NM * g.ph * g.pw;
@@ -500,7 +513,8 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     for (int c = 0; c < nchunk; ++c) {
         const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk), nb = b1 - b0;
         if (nb <= 0) continue;
-        VTI_CUDA(cudaMemcpyAsync(h->d_frames + b0 * fsz, frames + b0 * fsz, nb * fsz, cudaMemcpyHostToDevice, cs));
+        if (fmt == 1) VTI_CUDA(cudaMemcpyAsync(h->d_yuyv + b0 * ysz, frames + b0 * ysz, nb * ysz, cudaMemcpyHostToDevice, cs));
+        else VTI_CUDA(cudaMemcpyAsync(h->d_frames + b0 * fsz, frames + b0 * fsz, nb * fsz, cudaMemcpyHostToDevice, cs));
         for (int l = 0; l < 3; ++l)
             if (!zc_p[l])
                 VTI_CUDA(cudaMemcpyAsync(h->d_p[l] + b0 * lsz[l], hp[l] + b0 * lsz[l], sizeof(float) * nb * lsz[l],
@@ -512,6 +526,7 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
         VTI_CUDA(cudaEventRecord(h->chunk_ev[c], cs));
         VTI_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
         vti_det* cd = h->d_dets + (size_t)b0 * h->p.max_det;
+        if (fmt == 1 && (rc = vti_launch_k0_yuyv(h, h->d_yuyv + b0 * ysz, nb, h->d_frames + b0 * fsz, s))) return rc;
         if ((rc = vti_launch_k1(h, h->d_frames + b0 * fsz, nb, h->d_net_in + b0 * nsz, s))) return rc;
         if ((rc = vti_launch_k2(h, dev_p[0] + b0 * lsz[0], dev_p[1] + b0 * lsz[1], dev_p[2] + b0 * lsz[2], nb, s))) return rc;
         if ((rc = vti_launch_k3(h, dev_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
@@ -526,4 +541,16 @@ extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const floa
     }
     VTI_CUDA(cudaStreamSynchronize(s));
     return VTI_OK;
+}
+
+extern "C" int vti_process_host(vti_handle* h, const uint8_t* frames, const float* p3, const float* p4, const float* p5,
+                                const float* coef, const float* proto, int B, float* net_in, vti_det* dets,
+                                int32_t* counts, vti_frame_result* results) {
+    return process_host_impl(h, frames, 0, p3, p4, p5, coef, proto, B, net_in, dets, counts, results);
+}
+
+extern "C" int vti_process_host_yuyv(vti_handle* h, const uint8_t* yuyv, const float* p3, const float* p4, const float* p5,
+                                     const float* coef, const float* proto, int B, float* net_in, vti_det* dets,
+                                     int32_t* counts, vti_frame_result* results) {
+    return process_host_impl(h, yuyv, 1, p3, p4, p5, coef, proto, B, net_in, dets, counts, results);
 }

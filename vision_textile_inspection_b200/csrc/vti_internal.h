@@ -67,6 +67,7 @@ struct vti_handle {
     // ---- host-buffer path
     cudaStream_t own_stream, copy_stream;
     cudaEvent_t chunk_ev[4];
+    uint8_t* d_yuyv;                               // camera-native staging (vti_process_host_yuyv), allocated on first use
     uint8_t* d_frames; float* d_net_in; float* d_p[3]; float* d_coef; float* d_proto;
     vti_det* d_dets; int32_t* d_counts; vti_frame_result* d_results;
     size_t staged_batch;
@@ -92,6 +93,7 @@ int vti_raise_dyn_smem(const void* func, size_t bytes);
 int vti_k1_plan(vti_handle* h, const std::vector<int32_t>& xi, const std::vector<int32_t>& yi,
                 const std::vector<int16_t>& xa, const std::vector<int16_t>& yb,
                 const std::vector<int32_t>* und_ix, const std::vector<int32_t>* und_iy);
+int vti_launch_k0_yuyv(vti_handle* h, const uint8_t* yuyv, int B, uint8_t* frames, cudaStream_t s);
 int vti_launch_k1(vti_handle* h, const uint8_t* frames, int B, float* net_in, cudaStream_t s);
 int vti_launch_k2(vti_handle* h, const float* p3, const float* p4, const float* p5, int B, cudaStream_t s);
 int vti_launch_k3(vti_handle* h, const float* coef, int B, vti_det* dets, int32_t* counts, int all_dets, cudaStream_t s);

@@ -290,9 +290,25 @@ class InspectionEngine:
         """The WHOLE frame -- K1 -> backbone -> K2 -> K3 -> K4 -> K5 -- for a fixed batch as ONE CUDA graph."""
         return GraphedPipeline(self, backbone, B, export_masks)
 
+    def ingest_yuyv(self, yuyv: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """K0: camera-native packed YUV 4:2:2 frames (B,h,w,2) uint8 on the device -> (B,h,w,3) BGR, bit-exact against
+        cv2.cvtColor(.., COLOR_YUV2BGR_YUY2) (what cv2.VideoCapture.read() does on the CPU, main.py:188)."""
+        B = yuyv.shape[0]
+        self._chk(yuyv, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 2), "yuyv")
+        if out is None:
+            out = torch.empty((B, self.cfg.frame_h, self.cfg.frame_w, 3), dtype=torch.uint8, device=self.device)
+        self._chk(out, torch.uint8, (B, self.cfg.frame_h, self.cfg.frame_w, 3), "out")
+        with torch.cuda.device(self.device):
+            check(self.lib.vti_ingest_yuyv(self._h, yuyv.data_ptr(), B, out.data_ptr(), self._stream()), "vti_ingest_yuyv")
+        return out
+
     def process_host(self, frames: np.ndarray, p3, p4, p5, coef, proto, want_net_in: bool = False, out=None):
-        """End-to-end with HOST numpy buffers (ideally pinned): H2D, K1..K5, D2H.  Returns (dets, counts, results[, net_in])."""
+        """End-to-end with HOST numpy buffers (ideally pinned): H2D, K1..K5, D2H.  Returns (dets, counts, results[, net_in]).
+        `frames` is (B,h,w,3) BGR, or (B,h,w,2) camera-native YUYV (converted on the device by K0)."""
         B = frames.shape[0]
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[1:3] != (self.cfg.frame_h, self.cfg.frame_w) or frames.shape[3] not in (2, 3):
+            raise ValueError(f"process_host: frames must be uint8 (B,{self.cfg.frame_h},{self.cfg.frame_w},3) BGR or (..,2) YUYV, got {frames.dtype} {frames.shape}")
+        entry = self.lib.vti_process_host if frames.shape[3] == 3 else self.lib.vti_process_host_yuyv
         if out is None:
             out = (np.empty((B, self.cfg.max_det), DET_DTYPE), np.empty((B,), np.int32), np.empty((B,), RESULT_DTYPE))
         dets, counts, results = out
@@ -302,9 +318,9 @@ class InspectionEngine:
             if not a_.flags["C_CONTIGUOUS"]:
                 raise ValueError("process_host needs C-contiguous host arrays")
         with torch.cuda.device(self.device):
-            check(self.lib.vti_process_host(self._h, *[a_.ctypes.data for a_ in arrs], B,
-                                            net_in.ctypes.data if net_in is not None else None, dets.ctypes.data,
-                                            counts.ctypes.data, results.ctypes.data), "vti_process_host")
+            check(entry(self._h, *[a_.ctypes.data for a_ in arrs], B,
+                        net_in.ctypes.data if net_in is not None else None, dets.ctypes.data,
+                        counts.ctypes.data, results.ctypes.data), "vti_process_host")
         return (dets, counts, results, net_in) if want_net_in else (dets, counts, results)
 
     @property

@@ -300,3 +300,19 @@ def make_batch(cfg: WorkloadConfig, batch: int, seed0: int | None = None, n_uniq
     if with_frames:
         out["frames"] = np.stack([frames[i] for i in idx])
     return out
+
+
+def bgr_to_yuyv(bgr: np.ndarray) -> np.ndarray:
+    """A YUYV camera stand-in for tests and the bench: (h, w, 3) BGR -> (h, w, 2) packed YUYV (BT.601 studio range, chroma of a
+    pixel pair averaged).  Not an OpenCV restatement -- only the decode direction has a parity bar."""
+    f = bgr.astype(np.float64)
+    b, g, r = f[..., 0], f[..., 1], f[..., 2]
+    y = 16 + (65.481 * r + 128.553 * g + 24.966 * b) / 255
+    u = 128 + (-37.797 * r - 74.203 * g + 112.0 * b) / 255
+    v = 128 + (112.0 * r - 93.786 * g - 18.214 * b) / 255
+    out = np.empty(bgr.shape[:2] + (2,), np.uint8)
+    out[..., 0] = np.clip(np.rint(y), 0, 255)
+    out[:, 0::2, 1] = np.clip(np.rint((u[:, 0::2] + u[:, 1::2]) / 2), 0, 255)
+    out[:, 1::2, 1] = np.clip(np.rint((v[:, 0::2] + v[:, 1::2]) / 2), 0, 255)
+    return out
+
