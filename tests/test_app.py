@@ -87,6 +87,32 @@ def test_process_frame_reproduces_the_verbatim_reference_sequence(tmp_path):
 
 
 @pytest.mark.gpu
+def test_process_frame_takes_camera_native_yuyv_frames(tmp_path):
+    """the frame as the V4L2 camera delivers it (packed YUYV) -- K0 converts on the device; the
+    annotated frame is cv2's BGR decode of the same bytes, the network input is what K1 makes of that decode."""
+    import cv2
+    cfg = synth.CONFIGS["cfg2"]
+    cp, ep = write_calibration(tmp_path)
+    seen = []
+
+    class Spy(PlantedBackbone):
+        def __call__(self, net_in):
+            seen.append(net_in.clone())
+            return super().__call__(net_in)
+    bb = Spy(cfg)
+    app = A.StitchMeasurementApp(cp, ep, "best_Model.pt", camera_index=None, calib_w=cfg.frame_w, calib_h=cfg.frame_h,
+                                 backbone=bb, roi=cfg.roi(), imgsz=cfg.imgsz, annotate=False)
+    yuyv = synth.bgr_to_yuyv(synth.fabric_frame(cfg, 2003))
+    bgr = cv2.cvtColor(yuyv, cv2.COLOR_YUV2BGR_YUY2)
+    bb.queue += [2003, 2003]
+    a1, m1 = app.process_frame(yuyv)
+    a2, m2 = app.process_frame(bgr)
+    assert np.array_equal(a1, bgr) and np.array_equal(a2, bgr)
+    assert torch.equal(seen[0], seen[1])
+    assert m1["stitch_count"] == m2["stitch_count"] > 0 and "error" not in m1
+
+
+@pytest.mark.gpu
 def test_process_frame_error_paths_never_raise(tmp_path):
     cfg = synth.CONFIGS["native"]
     cp, ep = write_calibration(tmp_path)

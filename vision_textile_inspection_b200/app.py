@@ -144,9 +144,12 @@ class B200Predictor:
 
     @torch.no_grad()
     def run(self, frames: np.ndarray, conf, iou, max_det, imgsz, export_masks=True):
-        """frames (B,h,w,3) uint8 host array -> (engine, dets, counts, results, masks) with records on the host."""
+        """frames (B,h,w,3) uint8 BGR host array -- or (B,h,w,2) packed YUYV as a V4L2 camera delivers it -> (engine, dets,
+        counts, results, masks) with records on the host."""
         B, h, w = frames.shape[:3]
         eng = self.engine_for(h, w, imgsz, conf, iou, max_det, B)
+        if frames.shape[3] == 2 and self.use_graph:
+            raise ValueError("use_graph takes BGR frames; YUYV frames go through the stream path")
         if self.use_graph:
             key = (id(eng), B, bool(export_masks))
             pipe = self._pipes.get(key)
@@ -156,6 +159,8 @@ class B200Predictor:
             self.last_device = (eng, pipe.frames, dets, counts)
             return eng, eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results), masks
         d_frames = torch.from_numpy(np.ascontiguousarray(frames)).to(self.device, non_blocking=True)
+        if frames.shape[3] == 2:                                            # camera-native YUYV (main.py:188's cap.read()
+            d_frames = eng.ingest_yuyv(d_frames)                            # conversion, on the device): K0
         net_in = eng.preprocess(d_frames)                                   # K1
         p3, p4, p5, coef, proto = self.backbone(net_in)                     # PyTorch backbone -> raw head tensors
         dets, counts, results, masks = eng.post_measure(p3, p4, p5, coef, proto, export_masks=export_masks)  # K2..K5
@@ -275,7 +280,8 @@ class StitchMeasurementApp:
         return [self._finish(results[b]) for b in range(frames.shape[0])]
 
     def process_frame(self, frame):
-        """frame: h x w x 3 uint8 BGR (not mutated).  Returns (annotated, measurements); never raises."""
+        """frame: h x w x 3 uint8 BGR (not mutated), or h x w x 2 packed YUYV straight from the camera (converted on the
+        device, bit-exact cv2.cvtColor).  Returns (annotated BGR, measurements); never raises."""
         try:
             m = self.process_frames(np.ascontiguousarray(frame)[None])[0]
         except Exception as e:
@@ -284,7 +290,8 @@ class StitchMeasurementApp:
                                   "timestamp": datetime.now(), "error": "Model inference failed"}
         if self.annotate == "gpu":
             return self._annotate_gpu(frame, m), m
-        annotated = frame.copy()
+        # a YUYV frame comes back as the BGR frame K0 made of it on the device (what cap.read() would have returned)
+        annotated = frame.copy() if frame.shape[2] == 3 else self.model.last_device[1][0].cpu().numpy()
         if self.annotate:
             self._draw(annotated, m)
         return annotated, m
