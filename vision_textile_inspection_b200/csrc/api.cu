@@ -19,6 +19,7 @@ size_t vti_k3_smem_bytes(int cap);
 int vti_k3_prepare(int cap);
 int vti_k3_cap_pad(int cap);
 int vti_k4_prepare();
+int vti_k5_prepare(int max_det);
 
 static thread_local std::string g_err;
 void vti_set_error(const std::string& s) { g_err = s; }
@@ -315,7 +316,7 @@ extern "C" int vti_create(const vti_params* p, vti_handle** out) {
         vti_destroy(h);
         return VTI_ENOMEM;
     }
-    if ((rc = vti_k3_prepare(g.max_candidates)) || (rc = vti_k4_prepare())) { vti_destroy(h); return rc; }
+    if ((rc = vti_k3_prepare(g.max_candidates)) || (rc = vti_k4_prepare()) || (rc = vti_k5_prepare(h->p.max_det))) { vti_destroy(h); return rc; }
     *out = h;
     return VTI_OK;
 }

@@ -11,8 +11,12 @@
 // Spec / oracle: oracle/measure_port.py (pinned against the verbatim reference through tests/golden/).
 //
 // One CTA per frame.  Per-stitch work is thread-parallel; the order-dependent pieces (k-means, numpy's pairwise
-// summation order for np.mean, ordered list building) run on thread 0 so that results follow the reference's
-// floating-point evaluation order.  Compiled with --fmad=false: numpy / OpenCV do not fuse multiply-adds.
+// summation order for np.mean, ordered list building) run on warp 0 so that results follow the reference's
+// floating-point evaluation order.  The kernel is a latency chain, so the chain is kept short: while warp 0 iterates
+// the k-means, warps 1..7 compute EVERY stitch's width, envelope-proximity decision and edge distance speculatively
+// (pure functions of the stitch and the envelope) and the per-detection areas; the selection then only picks from
+// what is already there.  Shared memory is sized by max_det (14 KB at 200), so that a K5 CTA fits beside K1's.
+// Compiled with --fmad=false: numpy / OpenCV do not fuse multiply-adds.
 // The 8-frame temporal median (measurement.py:474-484) is frame-ordered state and stays on the host.
 #include <climits>
 
@@ -21,7 +25,6 @@
 namespace {
 
 constexpr int K5_THREADS = 256;
-constexpr int MAXN = 1024;
 
 struct Camera {
     double fx, fy, cx, cy, ifx, ify;
@@ -41,6 +44,7 @@ struct K5Args {
     int max_det, LW, w, h;
     int variant, min_stitches, max_px, nb;
     int mask_variant;
+    int cap;                   // entries per shared array: max_det rounded up to 8
 };
 
 __device__ __forceinline__ bool pixel_to_world(const Camera& c, double u, double v, double out[3]) {
@@ -156,17 +160,59 @@ __device__ __forceinline__ bool env_median(const int32_t* envf, int w, int cx_in
     return true;
 }
 
-__global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) {
-    // everything thread 0 walks sequentially lives in shared memory (global round trips were 70 % of v1's time)
-    __shared__ double s_cy[MAXN];
-    __shared__ double s_tmp[MAXN];
-    __shared__ double s_w[MAXN];          // per stitch: width_mm (NaN = none)
-    __shared__ double s_d[MAXN];          // per final entry: dist_mm (NaN = none)
-    __shared__ unsigned s_flags[MAXN];    // per detection
-    __shared__ short s_st[MAXN];          // stitch list -> det index
-    __shared__ short s_sel[MAXN];         // selected -> stitch index
-    __shared__ short s_fin[MAXN];
-    __shared__ unsigned char s_lab[MAXN], s_new[MAXN], s_pass[MAXN];
+// Area of every bitmap on the fabric plane (north-star "area"; spec: oracle/measure_port.py defect_area_mm2): m00 pixels x
+// the plane area of one pixel at the centroid, |dP/du x dP/dv| by central differences.  The four projections of a
+// detection run on four neighbouring lanes.  Called by whole warps: thread t of nt (both multiples of 32 apart).
+__device__ void areas(const K5Args& a, vti_det* __restrict__ dets, int n, int t, int nt, int lane) {
+    const Camera& cam = a.cam;
+    for (int base = 0; base < 4 * n; base += nt) {                   // warp-uniform trip count (shuffles below)
+        const int q4 = base + t, k = q4 >> 2, j = q4 & 3;
+        double p[3] = {0.0, 0.0, 0.0};
+        bool ok = false;
+        long long m00 = 0;
+        if (k < n) {
+            m00 = dets[k].m00;
+            if (m00 > 0) {
+                const double cx = (double)dets[k].m10 / (double)m00, cy = (double)dets[k].m01 / (double)m00;
+                ok = pixel_to_world(cam, cx + (j == 0 ? -0.5 : (j == 1 ? 0.5 : 0.0)), cy + (j == 2 ? -0.5 : (j == 3 ? 0.5 : 0.0)), p);
+            }
+        }
+        const int l0 = lane & ~3;
+        double q[4][3];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q[jj][c] = __shfl_sync(0xffffffffu, p[c], l0 + jj);
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (k < n && j == 0 && m00 > 0 && ((okm >> l0) & 0xFu) == 0xFu) {
+            const double ux = q[1][0] - q[0][0], uy = q[1][1] - q[0][1], uz = q[1][2] - q[0][2];
+            const double vx = q[3][0] - q[2][0], vy = q[3][1] - q[2][1], vz = q[3][2] - q[2][2];
+            const double c0 = uy * vz - uz * vy, c1 = uz * vx - ux * vz, c2 = ux * vy - uy * vx;
+            dets[k].area_mm2 = (double)m00 * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 1e6;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args a) {
+    // everything warp 0 walks sequentially lives in shared memory (global round trips were 70 % of v1's time); the
+    // arrays hold a.cap = max_det (rounded up to 8) entries each
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int N = a.cap;
+    double* s_cy = reinterpret_cast<double*>(s_raw);
+    double* s_tmp = s_cy + N;
+    double* s_w = s_tmp + N;              // per stitch: width_mm (NaN = none)
+    double* s_d = s_w + N;                // per final entry: dist_mm (NaN = none)
+    double* s_med = s_d + N;              // per stitch (speculative): envelope median at the stitch's column
+    double* s_dsp = s_med + N;            // per stitch (speculative): dist_mm (NaN = none)
+    double* s_wsp = s_dsp + N;            // per stitch (speculative, variant 1): width_mm (NaN = none)
+    unsigned* s_flags = reinterpret_cast<unsigned*>(s_wsp + N);   // per detection
+    short* s_st = reinterpret_cast<short*>(s_flags + N);          // stitch list -> det index
+    short* s_sel = s_st + N;                                      // selected -> stitch index
+    short* s_fin = s_sel + N;
+    unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_fin + N);
+    unsigned char* s_new = s_lab + N;
+    unsigned char* s_pass = s_new + N;    // per stitch (speculative): passes the envelope-proximity filter
+    unsigned char* s_mok = s_pass + N;    // per stitch (speculative): the envelope median exists
     __shared__ int s_ns, s_nsel, s_nfin, s_nfab, s_ndrop;
     __shared__ long long s_envsum;
     __shared__ int s_envcnt;
@@ -196,35 +242,6 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         }
         dets[k].flags = f;
         s_flags[k] = f;
-    }
-    // Area of every bitmap on the fabric plane (north-star "area"; spec: oracle/measure_port.py defect_area_mm2): m00 pixels x
-    // the plane area of one pixel at the centroid, |dP/du x dP/dv| by central differences.  The four projections of a
-    // detection run on four neighbouring lanes (fp64 division-heavy: this is the longest per-detection piece of K5).
-    for (int base = 0; base < 4 * n; base += K5_THREADS) {           // warp-uniform trip count (shuffles below)
-        const int t = base + tid, k = t >> 2, j = t & 3;
-        double p[3] = {0.0, 0.0, 0.0};
-        bool ok = false;
-        long long m00 = 0;
-        if (k < n) {
-            m00 = dets[k].m00;
-            if (m00 > 0) {
-                const double cx = (double)dets[k].m10 / (double)m00, cy = (double)dets[k].m01 / (double)m00;
-                ok = pixel_to_world(cam, cx + (j == 0 ? -0.5 : (j == 1 ? 0.5 : 0.0)), cy + (j == 2 ? -0.5 : (j == 3 ? 0.5 : 0.0)), p);
-            }
-        }
-        const int l0 = lane & ~3;
-        double q[4][3];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) q[jj][c] = __shfl_sync(0xffffffffu, p[c], l0 + jj);
-        const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        if (k < n && j == 0 && m00 > 0 && ((okm >> l0) & 0xFu) == 0xFu) {
-            const double ux = q[1][0] - q[0][0], uy = q[1][1] - q[0][1], uz = q[1][2] - q[0][2];
-            const double vx = q[3][0] - q[2][0], vy = q[3][1] - q[2][1], vz = q[3][2] - q[2][2];
-            const double c0 = uy * vz - uz * vy, c1 = uz * vx - ux * vz, c2 = ux * vy - uy * vx;
-            dets[k].area_mm2 = (double)m00 * sqrt(c0 * c0 + c1 * c1 + c2 * c2) * 1e6;
-        }
     }
     const int* __restrict__ env = a.env + (size_t)b * a.LW;
     for (int x = tid; x < a.w; x += K5_THREADS) envf[x] = env[a.xmap[x]];   // variant 1 keeps INT_MAX = none for now
@@ -297,10 +314,11 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
             r.status = (s_envcnt == 0 ? VTI_ST_NO_FABRIC : VTI_ST_NO_STITCH) | ovf;
             a.res[b] = r;
         }
+        areas(a, dets, n, tid, K5_THREADS, lane);
         return;
     }
 
-    // ---- per-stitch centroid / extent (measurement.py:302-330) and, variant 0, width of every stitch (:343-356)
+    // ---- per-stitch centroid / extent (measurement.py:302-330)
     for (int i = tid; i < ns; i += K5_THREADS) {
         vti_det& d = dets[s_st[i]];
         double cx, cy, left, right;
@@ -320,10 +338,6 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
         d.cx = cx; d.cy = cy; d.left_px = left; d.right_px = right;
         s_cy[i] = cy;
         s_w[i] = qnan;
-        if (a.variant == 0) {
-            double mm;
-            if (dist_mm(cam, left, cy, right, cy, &mm)) { d.width_mm = mm; s_w[i] = mm; }
-        }
     }
     __syncthreads();
 
@@ -390,29 +404,48 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
             nsel = ns;
         }
         if (lane == 0) s_nsel = nsel;
+    } else {
+        // ---- warps 1..7, while warp 0 selects the row: everything that is a pure function of one stitch and the envelope,
+        //      for EVERY stitch -- width (measurement.py:343-356), envelope-proximity decision (:409-430), edge distance
+        //      (:440-459) [+ variant 1's width of a final stitch] -- and the per-detection areas
+        const int t0 = tid - 32, NT = K5_THREADS - 32;
+        for (int i = t0; i < ns; i += NT) {
+            vti_det& d = dets[s_st[i]];
+            const double cx = d.cx, cy = d.cy, left = d.left_px, right = d.right_px;
+            double med, mm;
+            if (a.variant == 0) {
+                if (dist_mm(cam, left, cy, right, cy, &mm)) { d.width_mm = mm; s_w[i] = mm; }
+            }
+            bool ok = false;
+            if (env_median(envf, a.w, (int)rint(cx), a.nb, &med)) {
+                const double env_y = (double)(int)rint(med);
+                const double dd = cy - env_y;
+                ok = (a.variant == 0) ? (fabs(dd) < (double)a.max_px) : (dd > 0.0 && dd < (double)a.max_px);
+            }
+            s_pass[i] = ok;
+            const int cx_int = min(max((int)rint(cx), 0), a.w - 1);
+            const bool mok = env_median(envf, a.w, cx_int, a.nb, &med);
+            s_mok[i] = mok;
+            s_med[i] = mok ? med : qnan;
+            s_dsp[i] = (mok && dist_mm(cam, cx, cy, cx, med, &mm)) ? mm : qnan;
+            if (a.variant == 1) {
+                double wv = qnan;
+                if (dist_mm(cam, left, cy, right, cy, &mm)) wv = mm;
+                else if (dist_mm(cam, cx, cy, cx + 10.0, cy, &mm)) wv = ((right - left) / 10.0) * mm;
+                s_wsp[i] = wv;
+            }
+        }
+        areas(a, dets, n, t0, NT, lane);
     }
     __syncthreads();
     const int nsel = s_nsel;
 
-    // ---- envelope-proximity filter (measurement.py:409-430)
-    for (int j = tid; j < nsel; j += K5_THREADS) {
-        const vti_det& d = dets[s_st[s_sel[j]]];
-        const int cxr = (int)rint(d.cx);
-        double med;
-        bool ok = false;
-        if (env_median(envf, a.w, cxr, a.nb, &med)) {
-            const double env_y = (double)(int)rint(med);
-            const double dd = d.cy - env_y;
-            ok = (a.variant == 0) ? (fabs(dd) < (double)a.max_px) : (dd > 0.0 && dd < (double)a.max_px);
-        }
-        s_pass[j] = ok;
-    }
-    __syncthreads();
+    // ---- envelope-proximity filter (measurement.py:409-430): the decisions are there, warp 0 builds the ordered list
     if (tid < 32) {
         int nf = 0;
         for (int base = 0; base < nsel; base += 32) {
             const int j = base + lane;
-            const bool p = (j < nsel) && s_pass[j];
+            const bool p = (j < nsel) && s_pass[s_sel[j]];
             const unsigned msk = __ballot_sync(0xffffffffu, p);
             if (p) s_fin[nf + __popc(msk & ((1u << lane) - 1u))] = s_sel[j];
             nf += __popc(msk);
@@ -423,24 +456,20 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
     __syncthreads();
     const int nfin = s_nfin;
 
-    // ---- edge distances (measurement.py:440-459) [+ widths of the final stitches, variant 1]
+    // ---- edge distances (measurement.py:440-459) [+ widths of the final stitches, variant 1]: picked from what warps
+    //      1..7 computed for every stitch
     for (int j = tid; j < nfin; j += K5_THREADS) {
         const int i = s_fin[j];
         vti_det& d = dets[s_st[i]];
-        const int cx_int = min(max((int)rint(d.cx), 0), a.w - 1);
-        double med, mm;
-        s_d[j] = qnan;
-        if (env_median(envf, a.w, cx_int, a.nb, &med)) {
-            d.edge_y = med;
-            if (dist_mm(cam, d.cx, d.cy, d.cx, med, &mm)) { d.dist_mm = mm; s_d[j] = mm; }
+        const double dv = s_dsp[i];
+        s_d[j] = dv;
+        if (s_mok[i]) {
+            d.edge_y = s_med[i];
+            if (dv == dv) d.dist_mm = dv;
         }
         if (a.variant == 1) {
-            if (dist_mm(cam, d.left_px, d.cy, d.right_px, d.cy, &mm)) {
-                d.width_mm = mm; s_w[i] = mm;
-            } else if (dist_mm(cam, d.cx, d.cy, d.cx + 10.0, d.cy, &mm)) {
-                mm = ((d.right_px - d.left_px) / 10.0) * mm;
-                d.width_mm = mm; s_w[i] = mm;
-            }
+            const double wv = s_wsp[i];
+            if (wv == wv) { d.width_mm = wv; s_w[i] = wv; }
         }
     }
     __syncthreads();
@@ -487,6 +516,11 @@ __global__ void __launch_bounds__(K5_THREADS) k5_measure_kernel(const K5Args a) 
 
 }  // namespace
 
+// 7 double, 1 unsigned, 3 short and 4 byte arrays of max_det (rounded up to 8) entries
+size_t vti_k5_smem_bytes(int max_det) { return (size_t)((max_det + 7) & ~7) * (7 * 8 + 4 + 3 * 2 + 4); }
+
+int vti_k5_prepare(int max_det) { return vti_raise_dyn_smem((const void*)k5_measure_kernel, vti_k5_smem_bytes(max_det)); }
+
 int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vti_frame_result* res, cudaStream_t s) {
     K5Args a;
     a.dets = dets;
@@ -510,7 +544,8 @@ int vti_launch_k5(vti_handle* h, int B, vti_det* dets, const int32_t* counts, vt
     a.max_det = p.max_det; a.LW = h->g.LW; a.w = p.frame_w; a.h = p.frame_h;
     a.variant = p.variant; a.min_stitches = p.min_stitches; a.max_px = p.max_px_distance; a.nb = p.neighborhood;
     a.mask_variant = p.mask_variant;
-    k5_measure_kernel<<<B, K5_THREADS, 0, s>>>(a);
+    a.cap = (p.max_det + 7) & ~7;
+    k5_measure_kernel<<<B, K5_THREADS, vti_k5_smem_bytes(p.max_det), s>>>(a);
     h->launches++;
     VTI_CUDA(cudaGetLastError());
     return VTI_OK;
