@@ -77,59 +77,55 @@ __device__ __forceinline__ bool dist_mm(const Camera& c, double u0, double v0, d
     return true;
 }
 
-// numpy's pairwise summation (add.reduce on a contiguous float64 vector) -- same association order
-__device__ double np_sum(const double* a, int n) {
+// np.add.reduce on one warp, same association order as numpy's pairwise_sum (add.reduce on a contiguous float64
+// vector): the 8 partial sums r[j] of a <= 128-element block live in lanes 0..7, are combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), the tail is added sequentially, and longer vectors split at n/2 rounded down to a
+// multiple of 8.  Every lane returns the sum.  (Warp-uniform control flow.)  The <= 128 block -- every vector of the
+// configured scenes -- is inlined into the kernel (shared-memory loads, several in flight, no call frame: as a plain
+// recursive function it took 80 % of warp 0's time); longer vectors take the recursive path.
+__device__ __forceinline__ double np_block_warp(const double* a, int n, int lane) {      // n <= 128
     if (n < 8) {
         double r = 0.0;
         for (int i = 0; i < n; ++i) r += a[i];
         return r;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i];
-        return res;
+    const int nb = n & ~7;
+    double r = 0.0;
+    if (lane < 8) {
+        r = a[lane];
+        int i = 8 + lane;
+        for (; i + 24 < nb; i += 32) {                     // four loads in flight; the adds keep numpy's order
+            const double x0 = a[i], x1 = a[i + 8], x2 = a[i + 16], x3 = a[i + 24];
+            r += x0; r += x1; r += x2; r += x3;
+        }
+        for (; i < nb; i += 8) r += a[i];
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_sum(a, n2) + np_sum(a + n2, n - n2);
+    r += __shfl_down_sync(0xffffffffu, r, 1);
+    r += __shfl_down_sync(0xffffffffu, r, 2);
+    r += __shfl_down_sync(0xffffffffu, r, 4);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    double t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = (nb + k < n) ? a[nb + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (nb + k < n) r += t[k];
+    return r;
 }
 
-
-// np.add.reduce on one warp, same association order as numpy's pairwise_sum: the 8 partial sums r[j] of a <= 128-element
-// block live in lanes 0..7, are combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), the tail is added sequentially, and
-// longer vectors split at n/2 rounded down to a multiple of 8.  Every lane returns the sum.  (Warp-uniform control flow.)
-__device__ double np_sum_warp(const double* a, int n, int lane) {
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; ++i) r += a[i];
-        return r;
-    }
-    if (n <= 128) {
-        const int nb = n - (n % 8);
-        double r = 0.0;
-        if (lane < 8) {
-            r = a[lane];
-            for (int i = 8 + lane; i < nb; i += 8) r += a[i];
-        }
-        r += __shfl_down_sync(0xffffffffu, r, 1);
-        r += __shfl_down_sync(0xffffffffu, r, 2);
-        r += __shfl_down_sync(0xffffffffu, r, 4);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        for (int i = nb; i < n; ++i) r += a[i];
-        return r;
-    }
+__device__ __noinline__ double np_sum_warp_long(const double* a, int n, int lane) {
+    if (n <= 128) return np_block_warp(a, n, lane);
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return np_sum_warp(a, n2, lane) + np_sum_warp(a + n2, n - n2, lane);
+    return np_sum_warp_long(a, n2, lane) + np_sum_warp_long(a + n2, n - n2, lane);
+}
+
+__device__ __forceinline__ double np_sum_warp(const double* a, int n, int lane) {
+    return n <= 128 ? np_block_warp(a, n, lane) : np_sum_warp_long(a, n, lane);
 }
 
 // dst[0..m) = src[i] for the i in [0, n) with flag[i] == want, order preserved; returns m (one warp).
-__device__ int compact_warp(const double* src, const unsigned char* flag, int want, int n, double* dst, int lane) {
+__device__ __forceinline__ int compact_warp(const double* src, const unsigned char* flag, int want, int n, double* dst, int lane) {
     int m = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
@@ -244,7 +240,25 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args 
         s_flags[k] = f;
     }
     const int* __restrict__ env = a.env + (size_t)b * a.LW;
-    for (int x = tid; x < a.w; x += K5_THREADS) envf[x] = env[a.xmap[x]];   // variant 1 keeps INT_MAX = none for now
+    // envelope at frame columns (variant 1 keeps INT_MAX = none for now).  Two dependent global loads per column: four
+    // columns per thread are in flight at once, and the valid-row sum is taken from the registers (variant 0)
+    long long esum = 0;
+    int ecnt = 0;
+    for (int x0 = tid; x0 < a.w; x0 += 4 * K5_THREADS) {
+        int xi[4], e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int x = x0 + q * K5_THREADS; xi[q] = x < a.w ? __ldg(a.xmap + x) : 0; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[q] = env[xi[q]];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int x = x0 + q * K5_THREADS;
+            if (x < a.w) {
+                envf[x] = e[q];
+                if (e[q] >= 0 && e[q] != INT_MAX) { esum += e[q]; ++ecnt; }
+            }
+        }
+    }
     __syncthreads();
     if (a.variant == 1) {
         // mask-less fabric detection -> filled bbox rectangle (check_stitch_distance.py:331-334), upper envelope
@@ -260,24 +274,22 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args 
             __syncthreads();               // uniform: n and the flags are the same for every thread
         }
         __syncthreads();
-        for (int x = tid; x < a.w; x += K5_THREADS)
-            if (envf[x] == INT_MAX) envf[x] = -1;
+        esum = 0; ecnt = 0;                // the fallback may have changed columns: sum what is there now
+        for (int x = tid; x < a.w; x += K5_THREADS) {
+            int e = envf[x];
+            if (e == INT_MAX) { e = -1; envf[x] = -1; }
+            if (e >= 0) { esum += e; ++ecnt; }
+        }
         __syncthreads();
     }
     {
-        long long sum = 0;
-        int cnt = 0;
-        for (int x = tid; x < a.w; x += K5_THREADS) {
-            const int e = envf[x];
-            if (e >= 0) { sum += e; ++cnt; }
-        }
         for (int o = 16; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            esum += __shfl_xor_sync(0xffffffffu, esum, o);
+            ecnt += __shfl_xor_sync(0xffffffffu, ecnt, o);
         }
-        if (lane == 0 && cnt > 0) {
-            atomicAdd((unsigned long long*)&s_envsum, (unsigned long long)sum);
-            atomicAdd(&s_envcnt, cnt);
+        if (lane == 0 && ecnt > 0) {
+            atomicAdd((unsigned long long*)&s_envsum, (unsigned long long)esum);
+            atomicAdd(&s_envcnt, ecnt);
         }
     }
     // ---- routing (measurement.py:249-272): ordered stitch list, one warp, ballot compaction
