@@ -124,6 +124,64 @@ __device__ __forceinline__ double np_sum_warp(const double* a, int n, int lane) 
     return n <= 128 ? np_block_warp(a, n, lane) : np_sum_warp_long(a, n, lane);
 }
 
+// Two independent vectors at once (the two k-means clusters, distance and width averages): the same operations in the
+// same order per vector, the two dependency chains interleaved.  Both n <= 128.
+__device__ __forceinline__ void np_block_warp2(const double* a0, int n0, const double* a1, int n1, int lane, double& s0, double& s1) {
+    const int nb0 = n0 & ~7, nb1 = n1 & ~7;
+    double r0 = 0.0, r1 = 0.0;
+    if (lane < 8) {
+        if (nb0) r0 = a0[lane];
+        if (nb1) r1 = a1[lane];
+        const int nbm = max(nb0, nb1);
+        for (int i = 8 + lane; i < nbm; i += 8) {
+            if (i < nb0) r0 += a0[i];
+            if (i < nb1) r1 += a1[i];
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        r0 += __shfl_down_sync(0xffffffffu, r0, o);
+        r1 += __shfl_down_sync(0xffffffffu, r1, o);
+    }
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    r1 = __shfl_sync(0xffffffffu, r1, 0);
+    double t0[7], t1[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        t0[k] = (nb0 + k < n0) ? a0[nb0 + k] : 0.0;
+        t1[k] = (nb1 + k < n1) ? a1[nb1 + k] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if (nb0 + k < n0) r0 += t0[k];
+        if (nb1 + k < n1) r1 += t1[k];
+    }
+    s0 = r0; s1 = r1;
+}
+
+__device__ __forceinline__ void np_sum_warp2(const double* a0, int n0, const double* a1, int n1, int lane, double& s0, double& s1) {
+    if (n0 <= 128 && n1 <= 128) { np_block_warp2(a0, n0, a1, n1, lane, s0, s1); return; }
+    s0 = np_sum_warp(a0, n0, lane);
+    s1 = np_sum_warp(a1, n1, lane);
+}
+
+// dst0 <- the src[i] with flag[i] == 0, dst1 <- those with flag[i] == 1 (i in [0, n), order preserved): both clusters in one pass
+__device__ __forceinline__ void compact2_warp(const double* src, const unsigned char* flag, int n, double* dst0, double* dst1,
+                                              int& m0, int& m1, int lane) {
+    m0 = 0; m1 = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int f = (i < n) ? (int)flag[i] : 2;
+        const double v = (i < n) ? src[i] : 0.0;
+        const unsigned k0 = __ballot_sync(0xffffffffu, f == 0), k1 = __ballot_sync(0xffffffffu, f == 1);
+        if (f == 0) dst0[m0 + __popc(k0 & lt)] = v;
+        else if (f == 1) dst1[m1 + __popc(k1 & lt)] = v;
+        m0 += __popc(k0); m1 += __popc(k1);
+    }
+    __syncwarp();
+}
+
 // dst[0..m) = src[i] for the i in [0, n) with flag[i] == want, order preserved; returns m (one warp).
 __device__ __forceinline__ int compact_warp(const double* src, const unsigned char* flag, int want, int n, double* dst, int lane) {
     int m = 0;
@@ -365,6 +423,8 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args 
             }
             for (int i = lane; i < ns; i += 32) s_lab[i] = 0;
             __syncwarp();
+            bool lab_means = false;                          // (lm0, lm1) are the means of the groups s_lab describes
+            double lm0 = 0.0, lm1 = 0.0;
             for (int it = 0; it < 10; ++it) {
                 int ones = 0;
                 for (int base = 0; base < ns; base += 32) {
@@ -376,32 +436,42 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args 
                 __syncwarp();
                 bool stop = (ones == 0 || ones == ns);
                 double n0 = 0.0, n1 = 0.0;
+                bool means = false;                          // (n0, n1) are the cluster means of s_new
                 if (!stop) {
-                    int m = compact_warp(s_cy, s_new, 0, ns, s_tmp, lane);
-                    n0 = np_sum_warp(s_tmp, m, lane) / (double)m;
+                    int m0, m1;
+                    double t0, t1;
+                    compact2_warp(s_cy, s_new, ns, s_tmp, s_d, m0, m1, lane);      // s_d is free until the final list exists
+                    np_sum_warp2(s_tmp, m0, s_d, m1, lane, t0, t1);
                     __syncwarp();
-                    m = compact_warp(s_cy, s_new, 1, ns, s_tmp, lane);
-                    n1 = np_sum_warp(s_tmp, m, lane) / (double)m;
-                    __syncwarp();
+                    n0 = t0 / (double)m0; n1 = t1 / (double)m1;
+                    means = true;
                     stop = (n0 == c0 && n1 == c1);
-                    if (stop) { n0 = c0; n1 = c1; }
                 }
-                if (!stop || a.variant == 1)                 // the reference's break leaves the labels stale (variant 0)
+                if (!stop || a.variant == 1) {               // the reference's break leaves the labels stale (variant 0)
                     for (int i = lane; i < ns; i += 32) s_lab[i] = s_new[i];
+                    lab_means = means; lm0 = n0; lm1 = n1;
+                }
                 __syncwarp();
                 if (stop) break;
                 c0 = n0; c1 = n1;
             }
             int chosen = 0;
             {
+                // means of the two label groups: the k-means has them already whenever the labels are those of an
+                // iteration that computed its means (the usual exit); otherwise (first-iteration exits) compute them
                 const double fm = (double)s_envsum / (double)s_envcnt;
                 double m0 = 1e9, m1 = 1e9;
-                int m = compact_warp(s_cy, s_lab, 0, ns, s_tmp, lane);
-                if (m > 0) m0 = np_sum_warp(s_tmp, m, lane) / (double)m;
-                __syncwarp();
-                m = compact_warp(s_cy, s_lab, 1, ns, s_tmp, lane);
-                if (m > 0) m1 = np_sum_warp(s_tmp, m, lane) / (double)m;
-                __syncwarp();
+                if (lab_means) {
+                    m0 = lm0; m1 = lm1;
+                } else {
+                    int c_0, c_1;
+                    double t0, t1;
+                    compact2_warp(s_cy, s_lab, ns, s_tmp, s_d, c_0, c_1, lane);
+                    np_sum_warp2(s_tmp, c_0, s_d, c_1, lane, t0, t1);
+                    __syncwarp();
+                    if (c_0 > 0) m0 = t0 / (double)c_0;
+                    if (c_1 > 0) m1 = t1 / (double)c_1;
+                }
                 chosen = (fabs(m0 - fm) < fabs(m1 - fm)) ? 0 : 1;
             }
             for (int base = 0; base < ns; base += 32) {
@@ -503,24 +573,25 @@ __global__ void __launch_bounds__(K5_THREADS, 4) k5_measure_kernel(const K5Args 
     // ---- averages (measurement.py:469-472), numpy summation order, warp 0
     __syncthreads();
     if (tid < 32) {
-        // s_flag8 marks the valid entries so that compact_warp can gather them in order
+        // s_new / s_lab mark the valid entries so that compact_warp can gather them in order; the two sums run interleaved
         for (int j = lane; j < nfin; j += 32) s_new[j] = (s_d[j] == s_d[j]);
-        __syncwarp();
-        int m = compact_warp(s_d, s_new, 1, nfin, s_tmp, lane);
-        r.n_dist = m;
-        if (m >= a.min_stitches) r.avg_dist = np_sum_warp(s_tmp, m, lane) / (double)m;
-        __syncwarp();
+        const double* wsrc = s_w;
+        int wn = ns;
         if (a.variant == 0) {
-            for (int i = lane; i < ns; i += 32) s_new[i] = (s_w[i] == s_w[i]);
-            __syncwarp();
-            m = compact_warp(s_w, s_new, 1, ns, s_tmp, lane);
+            for (int i = lane; i < ns; i += 32) s_lab[i] = (s_w[i] == s_w[i]);
         } else {
-            for (int j = lane; j < nfin; j += 32) { const double wv = s_w[s_fin[j]]; s_cy[j] = wv; s_new[j] = (wv == wv); }
-            __syncwarp();
-            m = compact_warp(s_cy, s_new, 1, nfin, s_tmp, lane);
+            for (int j = lane; j < nfin; j += 32) { const double wv = s_w[s_fin[j]]; s_cy[j] = wv; s_lab[j] = (wv == wv); }
+            wsrc = s_cy; wn = nfin;
         }
-        r.n_width = m;
-        if (m >= a.min_stitches) r.avg_width = np_sum_warp(s_tmp, m, lane) / (double)m;
+        __syncwarp();
+        const int md = compact_warp(s_d, s_new, 1, nfin, s_tmp, lane);
+        const int mw = compact_warp(wsrc, s_lab, 1, wn, s_dsp, lane);          // s_dsp is free once the final list is written
+        double sd, sw;
+        np_sum_warp2(s_tmp, md, s_dsp, mw, lane, sd, sw);
+        r.n_dist = md;
+        if (md >= a.min_stitches) r.avg_dist = sd / (double)md;
+        r.n_width = mw;
+        if (mw >= a.min_stitches) r.avg_width = sw / (double)mw;
         r.status = VTI_ST_OK | ovf;
         if (lane == 0) a.res[b] = r;
     }
