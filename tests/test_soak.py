@@ -17,7 +17,9 @@ from vision_textile_inspection_b200.engine import EngineConfig, InspectionEngine
 
 pytestmark = pytest.mark.gpu
 N = int(os.environ.get("VTI_SOAK", "0"))
+MASKS = int(os.environ.get("VTI_SOAK_MASKS", "0"))       # 1: also export every mask and compare it with torch's, pixel by pixel
 MM_RTOL = 1e-3
+TIE_EPS = 1e-5
 
 
 def dev(a):
@@ -33,12 +35,14 @@ def test_soak(name, first, scale, calib):
     B = min(count, 16)
     eng = InspectionEngine(EngineConfig.for_workload(cfg, helpers.load_calib(), max_batch=B))
     rep = dict(config=name, scenes=0, detections=0, frames_ok=0, frames_no_fabric=0, frames_no_stitch=0, max_rel_mm=0.0)
+    if MASKS:
+        rep.update(mask_instances=0, mask_pixels=0, flipped_instances=0, flipped_pixels=0, max_flip_margin=0.0, min_iou_ge_1000px=1.0)
     for s0 in range(first, first + count, B):
         seeds = list(range(s0, min(s0 + B, first + count)))
         heads = [synth.planted_head(cfg, s) for s in seeds]
         lv = [dev(np.stack([h["levels"][l] for h in heads])) for l in range(3)]
-        dets, counts, results, _ = eng.post_measure(lv[0], lv[1], lv[2], dev(np.stack([h["coef"] for h in heads])),
-                                                    dev(np.stack([h["proto"] for h in heads])))
+        dets, counts, results, masks = eng.post_measure(lv[0], lv[1], lv[2], dev(np.stack([h["coef"] for h in heads])),
+                                                        dev(np.stack([h["proto"] for h in heads])), export_masks=bool(MASKS))
         dets, counts, results = eng.dets_to_numpy(dets), counts.cpu().numpy(), eng.results_to_numpy(results)
         for b, (seed, hd) in enumerate(zip(seeds, heads)):
             sp = post_spec.postprocess_spec(hd["levels"], hd["coef"], cfg.conf, cfg.iou, cfg.max_det, cfg.nc, cfg.LH,
@@ -47,7 +51,25 @@ def test_soak(name, first, scale, calib):
             assert n == len(sp["keep_anchor"]), (seed, n)
             assert np.array_equal(dets[b, :n]["anchor"], sp["keep_anchor"]), seed
             assert np.array_equal(dets[b, :n]["box_lb"].view(np.uint32), sp["box_lb"].view(np.uint32)), seed
-            _, res, m = helpers.oracle_scene(cfg, seed, calib)
+            _, res, m = helpers.oracle_scene(cfg, seed, calib, return_soft=bool(MASKS))
+            if MASKS and n:
+                ref = res.masks.data.numpy() > 0
+                got = eng.unpack_masks(masks, b, n).cpu().numpy() > 0
+                soft = res.soft.numpy()
+                for k in range(n):
+                    diff = np.logical_xor(got[k], ref[k])
+                    rep["mask_instances"] += 1
+                    rep["mask_pixels"] += int(ref[k].sum())
+                    if diff.any():      # only where torch's own value is within 1e-5 of the threshold
+                        margin = float(np.abs(soft[k][diff] - 0.5).max())
+                        rep["flipped_instances"] += 1
+                        rep["flipped_pixels"] += int(diff.sum())
+                        rep["max_flip_margin"] = max(rep["max_flip_margin"], margin)
+                        assert margin <= TIE_EPS, (seed, k, int(diff.sum()), margin)
+                    if ref[k].sum() >= 1000:
+                        iou = float((got[k] & ref[k]).sum()) / float((got[k] | ref[k]).sum())
+                        rep["min_iou_ge_1000px"] = min(rep["min_iou_ge_1000px"], iou)
+                        assert iou >= 0.999, (seed, k, iou)
             assert np.array_equal(dets[b, :n]["anchor"], res.keep_anchor), seed          # the real torchvision NMS
             r = results[b]
             assert (int(r["status"]) & 0xFF) == {"ok": 0, "no_fabric": 2, "no_stitch": 3}[m["status"]], (seed, m["status"])
@@ -63,7 +85,7 @@ def test_soak(name, first, scale, calib):
                         rel = abs(r[key] - ref) / ref
                         rep["max_rel_mm"] = max(rep["max_rel_mm"], float(rel))
                         assert rel <= MM_RTOL, (seed, key, r[key], ref)
-    path = os.path.join(helpers.ROOT, "gpurun_out", "soak_parity.json")
+    path = os.path.join(helpers.ROOT, "gpurun_out", "soak_masks.json" if MASKS else "soak_parity.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     allrep = json.load(open(path)) if os.path.exists(path) else {}
     allrep[name] = rep
