@@ -91,3 +91,40 @@ def test_soak(name, first, scale, calib):
     allrep[name] = rep
     json.dump(allrep, open(path, "w"), indent=1)
     print("soak", json.dumps(rep))
+
+
+@pytest.mark.skipif(N <= 0, reason="opt-in: set VTI_SOAK=<scenes per config>")
+def test_soak_k1_random_geometries():
+    """K1's planner (tile footprints, resize taps, undistort boxes, the generic fallback for widths that are not a
+    multiple of 8) over random frame sizes / imgsz / undistort: output bit-exact against real cv2 + torch every time."""
+    from oracle import cv_fixed, ultra_ref
+    calib = helpers.load_calib()
+    rng = np.random.default_rng(12345)
+    count = max(4, N // 4)
+    rep = dict(geometries=0, fast_path_widths=0, generic_widths=0, undistort_on=0, pixels=0)
+    for it in range(count):
+        h = int(rng.integers(48, 1400))
+        w = int(rng.integers(48, 2100))
+        if it % 3:
+            w &= ~7                                          # the fast path needs w % 8 == 0; every third width is arbitrary
+        imgsz = int(rng.choice([320, 480, 640, 960, 1280]))
+        undistort = int(rng.integers(0, 2))
+        flip = int(rng.integers(0, 2))
+        frames = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        K = cv_fixed.scale_K(np.array(calib["camera_matrix"]), w, h)
+        ec = EngineConfig(frame_h=h, frame_w=w, K=K, dist=np.array(calib["dist_coeffs"]), R=np.eye(3), t=np.array([0, 0, 0.1]),
+                          imgsz=imgsz, max_batch=2, undistort=undistort, channel_flip=flip, roi=(0, 0, 0, 0, 0))
+        eng = InspectionEngine(ec)
+        got = eng.preprocess(dev(frames)).cpu().numpy()
+        ref = ultra_ref.preprocess(list(frames), imgsz, undistort=(K, ec.dist) if undistort else None, flip_channels=bool(flip)).numpy()
+        assert got.shape == ref.shape, (h, w, imgsz, undistort, flip)
+        assert np.array_equal(got, ref), (h, w, imgsz, undistort, flip, int((got != ref).sum()))
+        rep["geometries"] += 1
+        rep["fast_path_widths" if w % 8 == 0 else "generic_widths"] += 1
+        rep["undistort_on"] += undistort
+        rep["pixels"] += int(got.size)
+        del eng
+    path = os.path.join(helpers.ROOT, "gpurun_out", "soak_k1.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    json.dump(rep, open(path, "w"), indent=1)
+    print("soak k1", json.dumps(rep))
