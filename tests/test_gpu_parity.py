@@ -630,6 +630,26 @@ def test_cuda_graph_step_replays_bit_identically():
             assert n > 0 and torch.equal(got[1][b, :n], rd[b, :n])
 
 
+def test_mask_variant_b_fused_path_drops_like_the_oracle(calib):
+    """Found by the soak run (tests/test_soak.py, VTI_SOAK_VARIANT_B=1): without mask export only ROUTED detections had
+    their masks evaluated, so in variant B every other detection looked empty and was flagged DROPPED.  Variant B now
+    evaluates all kept detections: the survivors are the oracle's, with and without export."""
+    cfg = synth.CONFIGS["cfg4"]
+    seed = 60000
+    hd = synth.planted_head(cfg, seed)
+    eng = make_engine(cfg, 1, mask_variant=1)
+    args = [dev(l[None]) for l in hd["levels"]] + [dev(hd["coef"][None]), dev(hd["proto"][None])]
+    _, res, m = helpers.oracle_scene(cfg, seed, calib, mask_variant="B")
+    for export in (False, True):
+        dets, counts, results, _ = eng.post_measure(*args, export_masks=export)
+        torch.cuda.synchronize()
+        n = int(counts[0])
+        d = eng.dets_to_numpy(dets)[0, :n]
+        kept = (d["flags"] & _lib.F_DROPPED) == 0
+        assert np.array_equal(d["anchor"][kept], res.keep_anchor.numpy()), export
+        assert eng.results_to_numpy(results)["n_det"][0] == kept.sum() == res.boxes.cls.shape[0]
+
+
 @pytest.mark.parametrize("name,seeds", [("cfg2", [2000, 2001]), ("cfg4", [4000]), ("native", [0])])
 def test_k4_tcgen05_tile_form_matches_unit_form(name, seeds):
     """vti_params.k4_dense = 2: the mask contraction on the tensor cores (tcgen05.mma kind::tf32, 3-term hi/lo split,

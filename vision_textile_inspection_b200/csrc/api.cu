@@ -396,7 +396,10 @@ extern "C" int vti_postprocess(vti_handle* h, const float* p3, const float* p4, 
     mark(h, 3, s);
     // (VTI_ALL_DETS: mask statistics for EVERY kept detection, not only routed stitch / fabric ones -- the dense-overlap
     //  experiments of tools/k4_dense_bench.py use many classes so that class-offset NMS keeps overlapping boxes)
-    if ((rc = vti_launch_k3(h, coef, B, dets, counts, masks != nullptr || getenv("VTI_ALL_DETS") != nullptr, s))) return rc;
+    // Mask variant B removes every detection whose mask is empty (newer Ultralytics, construct_result), routed or not: the
+    // masks of ALL kept detections are then evaluated so that the drop flags and n_det are the reference's.
+    if ((rc = vti_launch_k3(h, coef, B, dets, counts, masks != nullptr || h->p.mask_variant == 1 || getenv("VTI_ALL_DETS") != nullptr, s)))
+        return rc;
     mark(h, 4, s);
     rc = vti_launch_k4(h, proto, B, dets, counts, masks, s);
     mark(h, 5, s);
@@ -530,7 +533,7 @@ static int process_host_impl(vti_handle* h, const uint8_t* frames, int fmt, cons
         if (fmt == 1 && (rc = vti_launch_k0_yuyv(h, h->d_yuyv + b0 * ysz, nb, h->d_frames + b0 * fsz, s))) return rc;
         if ((rc = vti_launch_k1(h, h->d_frames + b0 * fsz, nb, h->d_net_in + b0 * nsz, s))) return rc;
         if ((rc = vti_launch_k2(h, dev_p[0] + b0 * lsz[0], dev_p[1] + b0 * lsz[1], dev_p[2] + b0 * lsz[2], nb, s))) return rc;
-        if ((rc = vti_launch_k3(h, dev_coef + b0 * csz, nb, cd, h->d_counts + b0, 0, s))) return rc;
+        if ((rc = vti_launch_k3(h, dev_coef + b0 * csz, nb, cd, h->d_counts + b0, h->p.mask_variant == 1, s))) return rc;
         if (map_proto && (rc = vti_launch_fetch_proto(h, map_proto + b0 * psz, h->d_proto + b0 * psz, nb, s))) return rc;
         if ((rc = vti_launch_k4(h, h->d_proto + b0 * psz, nb, cd, h->d_counts + b0, nullptr, s))) return rc;
         if ((rc = vti_launch_k5(h, nb, cd, h->d_counts + b0, h->d_results + b0, s))) return rc;
