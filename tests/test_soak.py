@@ -228,3 +228,31 @@ def _tie_margin(sp, iou_thr, conf_thr):
 def cv_scale(calib, imgsz):
     from oracle import cv_fixed
     return cv_fixed.scale_K(np.array(calib["camera_matrix"]), imgsz, imgsz)
+
+
+@pytest.mark.skipif(N <= 0, reason="opt-in: set VTI_SOAK=<scenes per config>")
+@pytest.mark.parametrize("name,first", [("cfg2", 21000), ("cfg4", 61000), ("cfg3", 31000)])
+def test_soak_host_path_equals_device_path(name, first):
+    """vti_process_host on pinned buffers (frames by DMA, head tensors read in place over PCIe, only the union rectangle
+    of the crop windows of the prototypes fetched) against the device-resident path on the same scenes: identical
+    record bytes, counts and frame results, chunk by chunk."""
+    cfg = synth.CONFIGS[name]
+    B = 16
+    rounds = max(1, N // 64)
+    eng = InspectionEngine(EngineConfig.for_workload(cfg, helpers.load_calib(), max_batch=B))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    rep = dict(config=name, scenes=0, detections=0)
+    for r in range(rounds):
+        batch = synth.make_batch(cfg, B, seed0=first + r * B)
+        keep = [pin(batch["frames"])] + [pin(l) for l in batch["levels"]] + [pin(batch["coef"]), pin(batch["proto"])]
+        d1, c1, r1, n1 = eng.process_host(*[t.numpy() for t in keep], want_net_in=True)
+        dv = [t.cuda() for t in keep]
+        n2 = eng.preprocess(dv[0]).cpu().numpy()
+        d2, c2, r2, _ = eng.post_measure(*dv[1:])
+        d2, c2, r2 = eng.dets_to_numpy(d2), c2.cpu().numpy(), eng.results_to_numpy(r2)
+        assert np.array_equal(n1, n2) and np.array_equal(c1, c2) and r1.tobytes() == r2.tobytes(), (name, r)
+        for b in range(B):
+            assert d1[b, :c1[b]].tobytes() == d2[b, :c2[b]].tobytes(), (name, r, b)
+        rep["scenes"] += B
+        rep["detections"] += int(c1.sum())
+    print("soak host", json.dumps(rep))
